@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the DXT1 / ETC1s block encoders on B200, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--codec dxt1|etc1]
+
+Workload (BASELINE.json configs[1]): synthetic 8192x8192 RGBA8 textures, device-resident.
+One "step" = one pass of the encoder over a batch of `--batch` distinct textures (default 4,
+1 GiB of input, so every launch streams far more than the 126 MB L2; inputs rotate).  With N
+GPUs every rank encodes its own batch (weak scaling, no data-path collective: blocks are
+independent); `value` = pixels all ranks encoded / max-over-ranks device time.
+
+One JSON line is printed by rank 0; see DESIGN.md "Measurement" for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BYTES_PER_PIXEL = 4.5  # algorithmic: 4 B RGBA read + 0.5 B block written
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--codec", choices=["dxt1", "etc1"], default="dxt1")
+    ap.add_argument("--size", type=int, default=8192, help="texture width = height")
+    ap.add_argument("--batch", type=int, default=4, help="distinct textures per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smmax, power, reasons = [], [], [], set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); smmax.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smmax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- synthetic input
+def fill_texture_device(torch, t, seed: int):
+    """Photo-like family S1 of SURVEY.md 8(d) (gradient + 4-bit noise), generated on the device:
+    byte(x, y, c) = ((x + y) / 8 + (rnd & 15) + 20 c) & 255, rnd from torch's Philox generator."""
+    h, w, _ = t.shape
+    g = torch.Generator(device=t.device)
+    g.manual_seed(seed)
+    yy = torch.arange(h, device=t.device, dtype=torch.int32).view(h, 1, 1)
+    xx = torch.arange(w, device=t.device, dtype=torch.int32).view(1, w, 1)
+    cc = (torch.arange(4, device=t.device, dtype=torch.int32) * 20).view(1, 1, 4)
+    rows = 1024
+    for y0 in range(0, h, rows):
+        y1 = min(h, y0 + rows)
+        noise = torch.randint(0, 16, (y1 - y0, w, 4), device=t.device, dtype=torch.int32, generator=g)
+        t[y0:y1] = (((xx + yy[y0:y1]) // 8 + noise + cc) & 255).to(torch.uint8)
+
+
+# ----------------------------------------------------------------------------- reference (CPU) arm
+def cpu_encode_rate(codec: int, size: int, threads: int, iters: int, ref, sample_rows: int | None = None):
+    """Best-of-`iters` MP/s of the reference encoder (row-parallel over `threads`) on a size x rows sample."""
+    from oracle.oracle import aligned_empty, synth_family
+
+    rows = sample_rows or size
+    img = aligned_empty(size * rows * 4)
+    tile = synth_family(1, size, min(rows, 256))
+    reps = (rows + tile.shape[0] - 1) // tile.shape[0]
+    img[:] = np.tile(tile.reshape(-1), reps)[: img.size]
+    out = np.zeros(size * rows // 2, dtype=np.uint8)
+    best = float("inf")
+    times = []
+    for _ in range(iters + 1):
+        t0 = time.perf_counter()
+        rc, _ = ref.compress_mt(codec, img, size, rows, size * 4, threads, out=out)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        times.append(dt)
+        best = min(best, dt)
+    return size * rows / best / 1e6, float(np.median(times[1:])) if len(times) > 1 else best
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref, built from the unmodified
+    reference sources) on this box's host cores, row-parallel over all hardware threads."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    from oracle.oracle import DXT1, ETC1, Oracle, Reference
+
+    codec = DXT1 if args.codec == "dxt1" else ETC1
+    size = args.size
+    if Reference.available():
+        ref, kind = Reference(), "reference"
+        threads = ref.hardware_threads() or os.cpu_count() or 1
+    else:  # the oracle port, single thread
+        ref, kind, threads = None, "port", 1
+
+    from oracle.oracle import aligned_empty, synth_family
+    img = aligned_empty(size * size * 4)
+    tile = synth_family(1, size, 256)
+    img[:] = np.tile(tile.reshape(-1), size // 256)
+    out = np.zeros(size * size // 2, dtype=np.uint8)
+
+    def one_step():
+        if ref is not None:
+            rc, _ = ref.compress_mt(codec, img, size, size, size * 4, threads, out=out)
+        else:
+            rc, _ = Oracle().compress(codec, img, size, size)
+        assert rc == 0
+
+    for _ in range(args.warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    mps = size * size * args.steps / dt / 1e6
+    sample = f"{args.steps} x one {size}x{size} RGBA8 texture ({args.codec}), row-parallel over {threads} threads"
+    line = {
+        "impl": "reference",
+        "metric": f"MP/s {args.codec.upper()} encode, {size}x{size} RGBA8",
+        "value": mps, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"synthetic {size}x{size} RGBA8 {args.codec.upper()}, host-resident, CPU reference",
+                   "codec": args.codec, "texture": [size, size]},
+        "cpu_baseline": {"value": mps, "unit": "MP/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": mps, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200_arm(args):
+    import torch
+
+    import goofy_b200 as gb
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    codec = gb.DXT1 if args.codec == "dxt1" else gb.ETC1
+    size, batch = args.size, args.batch
+    stride = size * 4
+    out_bytes = size * size // 2
+    px_per_step = size * size * batch
+
+    # device-resident inputs: `batch` distinct textures per rank, contiguous (uniform-batch layout)
+    src = torch.empty((batch, size, size, 4), dtype=torch.uint8, device=dev)
+    dst = torch.empty((batch, out_bytes), dtype=torch.uint8, device=dev)
+    for b in range(batch):
+        fill_texture_device(torch, src[b], seed=1000 * rank + b)
+    torch.cuda.synchronize()
+
+    def step(c=codec):
+        # one launch per texture: the launch a caller of the device API makes for one 8192^2 texture
+        for b in range(batch):
+            gb.check(gb.encode_device(c, dst[b], src[b], size, size, stride))
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = gb.kernel_launches()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = gb.kernel_launches() - l0
+        if distributed:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_px = px_per_step * args.steps * world
+    value = total_px / (ms * 1e-3) / 1e6
+    launch_ms = ms / (args.steps * batch)
+    achieved = size * size * BYTES_PER_PIXEL / (launch_ms * 1e-3) / 1e9
+    peak, peak_src = hbm_peak()
+
+    # the other codec, same protocol (BASELINE.json's metric names both)
+    other = gb.ETC1 if codec == gb.DXT1 else gb.DXT1
+    ms_o, _ = timed(lambda: step(other), max(args.steps // 2, 3), 3)
+    value_o = px_per_step * max(args.steps // 2, 3) * world / (ms_o * 1e-3) / 1e6
+    achieved_o = value_o / world * 1e6 * BYTES_PER_PIXEL / 1e9
+
+    # dual-output pass: both codecs from one read (5 B/px)
+    dst2 = torch.empty((batch, out_bytes), dtype=torch.uint8, device=dev)
+
+    def dual_step():
+        for b in range(batch):
+            gb.check(gb.encode_dual_device(dst[b], dst2[b], src[b], size, size, stride))
+    ms_d, _ = timed(dual_step, max(args.steps // 2, 3), 3)
+    value_d = px_per_step * max(args.steps // 2, 3) * world / (ms_d * 1e-3) / 1e6
+
+    # ---- end to end through the drop-in host API: pinned host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_src = torch.empty((size, size, 4), dtype=torch.uint8).pin_memory()
+        h_dst = torch.empty((out_bytes,), dtype=torch.uint8).pin_memory()
+        h_src.copy_(src[0].cpu())
+        host_fn = gb.compressDXT1 if codec == gb.DXT1 else gb.compressETC1
+
+        def e2e_step():
+            gb.check(host_fn(h_dst, h_src, size, size, stride))
+        e2e_steps = max(3, min(args.steps, 10))
+        ms_e, _ = timed(e2e_step, e2e_steps, 3)
+        e2e = {"value": size * size * e2e_steps * world / (ms_e * 1e-3) / 1e6, "unit": "MP/s",
+               "h2d_bytes_per_step": size * size * 4, "d2h_bytes_per_step": out_bytes,
+               "ms_per_step": ms_e / e2e_steps,
+               "api": f"goofy_b200.compress{args.codec.upper()}(result, input, w, h, stride) on pinned host buffers"}
+        # the result must be the same bytes the device-resident path produced
+        gb.check(gb.encode_device(codec, dst[0], src[0], size, size, stride))
+        torch.cuda.synchronize()
+        e2e["matches_device_path"] = bool(torch.equal(dst[0].cpu(), h_dst))
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only): the unmodified reference
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.oracle import Oracle, Reference
+        if Reference.available():
+            ref = Reference()
+            T = ref.hardware_threads() or os.cpu_count() or 1
+            one, _ = cpu_encode_rate(codec, size, 1, 6, ref)
+            allc, _ = cpu_encode_rate(codec, size, T, 8, ref)
+            cpu = {"value": allc, "unit": "MP/s", "cores": T, "kind": "reference",
+                   "sample": f"one {size}x{size} texture, best of 8, goofy::compress{args.codec.upper()} (-O2 -msse2) "
+                             f"row-parallel over {T} threads",
+                   "single_thread": {"value": one, "cores": 1, "sample": f"same texture, best of 6, as shipped"}}
+        else:
+            o = Oracle()
+            img = src[0, :1024].cpu().numpy()
+            t0 = time.perf_counter()
+            o.compress(codec, img, size, 1024)
+            dtc = time.perf_counter() - t0
+            cpu = {"value": size * 1024 / dtc / 1e6, "unit": "MP/s", "cores": 1, "kind": "port",
+                   "sample": f"{size}x1024 strip, one pass of the scalar oracle"}
+
+    if rank == 0:
+        line = {
+            "metric": f"MP/s {args.codec.upper()} encode, {size}x{size} RGBA8, device-resident",
+            "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"synthetic {size}x{size} RGBA8 {args.codec.upper()}, device-resident "
+                                   f"(BASELINE.json configs[{1 if args.codec == 'dxt1' else 2}])",
+                       "codec": args.codec, "texture": [size, size], "textures_per_step": batch,
+                       "pixels_per_step_per_gpu": px_per_step, "stride": stride,
+                       "l2": f"inputs larger than L2: {batch} distinct {size * size * 4 >> 20} MiB textures rotate, "
+                             f"each launch streams {int(size * size * BYTES_PER_PIXEL) >> 20} MiB",
+                       "sharding": "one batch per rank, no collectives" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "kernel": f"encode_direct_kernel<{args.codec}>", "bytes_per_launch": size * size * BYTES_PER_PIXEL,
+                         "launch_ms": launch_ms},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "other_codec": {"codec": "etc1" if codec == gb.DXT1 else "dxt1", "value": value_o, "unit": "MP/s",
+                            "achieved_gbs_per_gpu": achieved_o, "frac": achieved_o / peak},
+            "dual_output": {"value": value_d, "unit": "MP/s (each pixel encoded to both DXT1 and ETC1s)",
+                            "achieved_gbs_per_gpu": value_d / world * 1e6 * 5.0 / 1e9},
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

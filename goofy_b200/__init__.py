@@ -1,0 +1,20 @@
+"""goofy_b200 -- B200 (sm_100a) implementation of Goofy's DXT1/BC1 and ETC1s block encoders.
+
+Public surface (mirrors GoofyTC/goofy_tc.h:10-13 plus the batched device-resident variants):
+    compressDXT1, compressETC1                       drop-in host API, same signature and codes
+    encode_device, encode_batch_uniform_device,
+    encode_dual_device, encode_batch_device          device-resident, asynchronous
+    encode_sharded_host, encode_batch_sharded        multi-GPU, no collectives
+The implementation is libgoofy_b200.so (CUDA only; there is no CPU fallback).
+"""
+from .api import (DXT1, ETC1, CODEC_NAMES, GoofyError, check, compressDXT1, compressETC1, device_count,
+                  encode_batch_device, encode_batch_sharded, encode_batch_uniform_device, encode_device,
+                  encode_dual_device, encode_host, encode_sharded_host, error_string, kernel_launches,
+                  make_descriptors, output_bytes, strip_partition)
+
+__all__ = [
+    "DXT1", "ETC1", "CODEC_NAMES", "GoofyError", "check", "compressDXT1", "compressETC1", "device_count",
+    "encode_batch_device", "encode_batch_sharded", "encode_batch_uniform_device", "encode_device",
+    "encode_dual_device", "encode_host", "encode_sharded_host", "error_string", "kernel_launches",
+    "make_descriptors", "output_bytes", "strip_partition",
+]

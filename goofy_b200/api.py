@@ -1,0 +1,170 @@
+"""Host-side mirror of the reference's encoder interface, on top of the C ABI.
+
+Reference surface mirrored (GoofyTC/goofy_tc.h:10-13):
+    int goofy::compressDXT1(unsigned char* result, const unsigned char* input,
+                            unsigned width, unsigned height, unsigned stride);
+    int goofy::compressETC1(... same ...);
+Same names, same argument order and meaning (stride in BYTES, result holds width*height/2 bytes),
+same return codes (0, -1 width%16, -2 height%4) -- plus the new negative codes of
+include/goofy_b200.h.  Host buffers are numpy uint8 arrays (or anything exposing a writable
+buffer); device buffers are torch CUDA tensors or raw integer device pointers.  torch is only
+used to find a tensor's data_ptr / current stream: it is plumbing, not the encoder.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import GoofyB200Image
+
+DXT1 = 0
+ETC1 = 1
+CODEC_NAMES = {DXT1: "dxt1", ETC1: "etc1"}
+
+
+class GoofyError(RuntimeError):
+    def __init__(self, code: int):
+        self.code = code
+        super().__init__(f"goofy_b200 error {code}: {error_string(code)}")
+
+
+def error_string(code: int) -> str:
+    return _lib.load().goofy_b200_error_string(int(code)).decode()
+
+
+def device_count() -> int:
+    return int(_lib.load().goofy_b200_device_count())
+
+
+def kernel_launches() -> int:
+    return int(_lib.load().goofy_b200_kernel_launches())
+
+
+def output_bytes(width: int, height: int) -> int:
+    return width * height // 2
+
+
+# ------------------------------------------------------------------ pointer plumbing
+def _host_ptr(a, writable: bool) -> int:
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.uint8 or not a.flags["C_CONTIGUOUS"]:
+            raise TypeError("host buffers must be C-contiguous uint8 arrays")
+        if writable and not a.flags["WRITEABLE"]:
+            raise TypeError("result buffer is read-only")
+        return a.ctypes.data
+    if a is None:
+        return 0
+    if hasattr(a, "data_ptr"):  # torch CPU tensor (e.g. pinned)
+        if a.is_cuda:
+            raise TypeError("device tensor passed to the host API")
+        return int(a.data_ptr())
+    return int(a)
+
+
+def _dev_ptr(t) -> int:
+    if t is None:
+        return 0
+    if hasattr(t, "data_ptr"):
+        if not t.is_cuda:
+            raise TypeError("host tensor passed to the device API")
+        return int(t.data_ptr())
+    return int(t)
+
+
+def _stream_ptr(stream) -> int:
+    if stream is None:
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                return int(torch.cuda.current_stream().cuda_stream)
+        except ImportError:
+            pass
+        return 0
+    if hasattr(stream, "cuda_stream"):
+        return int(stream.cuda_stream)
+    return int(stream)
+
+
+# ------------------------------------------------------------------ drop-in host API
+def compressDXT1(result, input, width: int, height: int, stride: int) -> int:
+    """goofy::compressDXT1 (GoofyTC/goofy_tc.h:1497).  Returns the status code; never raises on bad shapes."""
+    return int(_lib.load().goofy_b200_compress_dxt1(_host_ptr(result, True), _host_ptr(input, False),
+                                                    width, height, stride))
+
+
+def compressETC1(result, input, width: int, height: int, stride: int) -> int:
+    """goofy::compressETC1 (GoofyTC/goofy_tc.h:1528)."""
+    return int(_lib.load().goofy_b200_compress_etc1(_host_ptr(result, True), _host_ptr(input, False),
+                                                    width, height, stride))
+
+
+def encode_host(codec: int, result, input, width: int, height: int, stride: int) -> int:
+    return int(_lib.load().goofy_b200_encode_host(codec, _host_ptr(result, True), _host_ptr(input, False),
+                                                  width, height, stride))
+
+
+def encode_sharded_host(codec: int, result, input, width: int, height: int, stride: int, n_gpus: int = 0) -> int:
+    """One host image, horizontal strips of whole block rows, strip g on GPU g (no collectives)."""
+    return int(_lib.load().goofy_b200_encode_sharded_host(codec, _host_ptr(result, True), _host_ptr(input, False),
+                                                          width, height, stride, n_gpus))
+
+
+# ------------------------------------------------------------------ device-resident API
+def encode_device(codec: int, d_result, d_input, width: int, height: int, stride: int, stream=None) -> int:
+    """Asynchronous on `stream` (default: torch's current stream)."""
+    return int(_lib.load().goofy_b200_encode_device(codec, _dev_ptr(d_result), _dev_ptr(d_input), width, height,
+                                                    stride, _stream_ptr(stream)))
+
+
+def encode_batch_uniform_device(codec: int, d_result, d_input, width: int, height: int, stride: int,
+                                input_image_pitch: int, result_image_pitch: int, n_images: int, stream=None) -> int:
+    return int(_lib.load().goofy_b200_encode_batch_uniform_device(
+        codec, _dev_ptr(d_result), _dev_ptr(d_input), width, height, stride, input_image_pitch,
+        result_image_pitch, n_images, _stream_ptr(stream)))
+
+
+def encode_dual_device(d_result_dxt1, d_result_etc1, d_input, width: int, height: int, stride: int,
+                       input_image_pitch: int = 0, result_image_pitch: int = 0, n_images: int = 1, stream=None) -> int:
+    """DXT1 and ETC1s from one read of the input."""
+    return int(_lib.load().goofy_b200_encode_dual_device(
+        _dev_ptr(d_result_dxt1), _dev_ptr(d_result_etc1), _dev_ptr(d_input), width, height, stride,
+        input_image_pitch, result_image_pitch, n_images, _stream_ptr(stream)))
+
+
+def make_descriptors(images: Iterable[Sequence]) -> C.Array:
+    """images: iterable of (d_src, d_dst, width, height, stride[, device]) -> GoofyB200Image[n]."""
+    items = list(images)
+    arr = (GoofyB200Image * len(items))()
+    for i, it in enumerate(items):
+        src, dst, w, h, stride = it[:5]
+        dev = it[5] if len(it) > 5 else -1
+        arr[i] = GoofyB200Image(_dev_ptr(src), _dev_ptr(dst), w, h, stride, dev)
+    return arr
+
+
+def encode_batch_device(codec: int, images, stream=None) -> int:
+    """Ragged batch on the current device, one launch."""
+    descs = images if isinstance(images, C.Array) else make_descriptors(images)
+    return int(_lib.load().goofy_b200_encode_batch_device(codec, descs, len(descs), _stream_ptr(stream)))
+
+
+def encode_batch_sharded(codec: int, images) -> int:
+    """Ragged batch whose images live on several GPUs of this process; returns after all devices finish."""
+    descs = images if isinstance(images, C.Array) else make_descriptors(images)
+    return int(_lib.load().goofy_b200_encode_batch_sharded(codec, descs, len(descs)))
+
+
+def strip_partition(height: int, n_shards: int, shard: int) -> tuple[int, int]:
+    """(first_block_row, block_row_count) of `shard` -- the scheduler's own partition function."""
+    first, count = C.c_uint32(), C.c_uint32()
+    _lib.load().goofy_b200_strip_partition(height, n_shards, shard, C.byref(first), C.byref(count))
+    return first.value, count.value
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise GoofyError(code)

@@ -1,0 +1,186 @@
+// block_codec.cuh -- one thread encodes one 4x4 block held in 16 registers.
+//
+// What is computed is exactly what the reference's SSE2 tile kernel computes per block
+// (GoofyTC/goofy_tc.h:1069-1494); how it is computed is different.  The reference spends
+// most of its instructions on byte unpack/transposes that exist only because it processes a
+// 16x4 tile across 16 byte lanes.  Here each thread owns a whole block, so the pipeline is
+// re-derived on two 16-bit lanes per register with closed forms whose equivalence to the
+// reference's rounded cascades is proven exhaustively in tests/test_closed_forms.py:
+//
+//   Y(R,G,B) = avg(avg(R,B),G)              == (R + 2G + B + 3) >> 2        (goofy_tc.h:1166,1205)
+//   to5(v)   = avg(avg(avg(sat-(v,8),0),0),0) == (max(v,1) - 1) >> 3        (goofy_tc.h:1309-1311,1462)
+//   qt       = sat+(quarter, eighth)        == ((r+3)>>2) + ((r+7)>>3)      (goofy_tc.h:1184-1190)
+//   avg(a,b) = (a+b+1)>>1                   == ~floor_avg(~a,~b), per byte  (goofy_tc.h:645-654)
+//
+// Pixel classification never shifts Y down: with S = R+2G+B+3 (one IDP.4A per pixel) and
+// e = S - 4*mid, the reference's masks (goofy_tc.h:1212-1224) become
+//   Gez  <=> e >= 0                     Lqt  <=> 4 - 4qt <= e < 4qt
+// Two pixels share a register as biased u16 lanes (lane = e + 0x4000); each test is then a
+// packed add whose carry lands in bit 14/15 of the lane.
+#pragma once
+#include "lanes.cuh"
+
+namespace gb {
+
+constexpr uint32_t kLuma = 0x00010201u;  // dp4a weights for bytes (R,G,B,A): R + 2G + B
+
+// min / max of 16 words, two u16 lanes each, in 8 three-input ops
+template <bool kMax>
+GB_DEV uint32_t reduce16(const uint32_t (&v)[16])
+{
+    auto m3 = [](uint32_t a, uint32_t b, uint32_t c) { return kMax ? max3_u16x2(a, b, c) : min3_u16x2(a, b, c); };
+    const uint32_t t0 = m3(v[0], v[1], v[2]);
+    const uint32_t t1 = m3(v[3], v[4], v[5]);
+    const uint32_t t2 = m3(v[6], v[7], v[8]);
+    const uint32_t t3 = m3(v[9], v[10], v[11]);
+    const uint32_t t4 = m3(v[12], v[13], v[14]);
+    const uint32_t t5 = m3(t0, t1, v[15]);
+    const uint32_t t6 = m3(t2, t3, t4);
+    return kMax ? max2_u16x2(t5, t6) : min2_u16x2(t5, t6);
+}
+
+// Everything the two codecs share: bounding box and the per-block brightness scalars.
+struct BlockFront {
+    // A u16 lane compare orders by its HIGH byte first, so the raw pixel word (lanes G:R | A:B)
+    // yields min/max G in byte 1, and the word shifted left by 8 (lanes R:0 | B:G) yields
+    // min/max R in byte 1 and min/max B in byte 3.  No per-channel unpack is needed.
+    uint32_t mnG, mxG;    // byte1 = min / max G
+    uint32_t mnRB, mxRB;  // byte1 = min / max R, byte3 = min / max B, byte0 = 0
+    uint32_t range;       // max(maxY - minY, 8)                  goofy_tc.h:1176
+    uint32_t mid;         // avg(minY, maxY)                      goofy_tc.h:1179
+    uint32_t laneBias;    // dp4a accumulator that makes lane = (R+2G+B+3) - 4*mid + 0x4000
+    uint32_t kLo, kHi;    // packed add constants: bit15 of (lane + kLo) <=> e >= 4 - 4qt, of (lane + kHi) <=> e >= 4qt
+};
+
+GB_DEV BlockFront analyse(const uint32_t (&p)[16])
+{
+    BlockFront f;
+    uint32_t q[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) q[i] = p[i] << 8;
+    f.mnG = reduce16<false>(p);
+    f.mxG = reduce16<true>(p);
+    f.mnRB = reduce16<false>(q);
+    f.mxRB = reduce16<true>(q);
+
+    // brightness of the two box corners (goofy_tc.h:1151-1171)
+    const uint32_t mnPix = prmt(f.mnRB, f.mnG, 0x3351);  // bytes (minR, minG, minB, .)
+    const uint32_t mxPix = prmt(f.mxRB, f.mxG, 0x3351);
+    const uint32_t minY = dp4a(mnPix, kLuma, 3u) >> 2;
+    const uint32_t maxY = dp4a(mxPix, kLuma, 3u) >> 2;
+
+    const uint32_t spread = maxY - minY;
+    f.range = spread > 8u ? spread : 8u;
+    f.mid = (minY + maxY + 1u) >> 1;
+    const uint32_t qt = ((f.range + 3u) >> 2) + ((f.range + 7u) >> 3);  // 3..96, goofy_tc.h:1184-1190
+
+    const uint32_t q4 = qt << 2;
+    f.laneBias = 0x4003u - (f.mid << 2);
+    f.kLo = (0x3FFCu + q4) * 0x10001u;
+    f.kHi = (0x4000u - q4) * 0x10001u;
+    return f;
+}
+
+// Two pixels -> one register of biased brightness lanes (low lane = a, high lane = b).
+GB_DEV uint32_t lanes_of(uint32_t a, uint32_t b, uint32_t laneBias)
+{
+    const uint32_t hi = dp4a(b, kLuma, laneBias);
+    return dp4a(a, kLuma, hi * 65536u + laneBias);
+}
+
+// bit15 of each lane <=> Lqt (|Y - mid| < qt)
+GB_DEV uint32_t lqt_lanes(uint32_t e, const BlockFront& f) { return (e + f.kLo) ^ (e + f.kHi); }
+
+// ---------------------------------------------------------------------------------------- DXT1
+// Output (goofy_tc.h:1276-1357): word0 = c0 | c1 << 16 with c0 = max corner 565 | 0x20,
+// c1 = min corner 565 (both with the green LSB cleared); word1 = 2 bits per pixel, row major,
+// bit0 = !Gez, bit1 = Lqt.
+GB_DEV void encode_dxt1(const uint32_t (&p)[16], const BlockFront& f, uint32_t& word0, uint32_t& word1)
+{
+    // low lane walks pixels 0..7, high lane pixels 8..15; each step pushes 2 bits per lane
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t e = lanes_of(p[i], p[i + 8], f.laneBias);
+        const uint32_t x = lqt_lanes(e, f);
+        const uint32_t z = bitsel(x, ~e, 0x80008000u);  // bit15 = Lqt, bit14 = !Gez
+        acc = bitsel(z, acc >> 2, 0xC000C000u);
+    }
+    word1 = acc;
+
+    // 888 -> 565 for both corners at once: low lane = max corner, high lane = min corner.
+    // to5 sits in the top 5 bits of a lane holding (max(v,1)-1) << 8.
+    uint32_t rr = prmt(f.mxRB, f.mnRB, 0x5010);  // (0, maxR, 0, minR)
+    uint32_t bb = prmt(f.mxRB, f.mnRB, 0x7030);  // (0, maxB, 0, minB)
+    uint32_t gg = prmt(f.mxG, f.mnG, 0x5410);    // (., maxG, ., minG)
+    rr = max2_u16x2(rr, 0x01000100u) - 0x01000100u;
+    gg = max2_u16x2(gg, 0x01000100u) - 0x01000100u;
+    // the odd constant also sets bit 16, which the >> 11 below turns into c0's forced green LSB (0x20)
+    bb = max2_u16x2(bb, 0x01000100u) - 0x00FF0100u;
+    const uint32_t rg = bitsel(rr, gg >> 5, 0xF800F800u);
+    word0 = bitsel(rg, bb >> 11, 0xFFC0FFC0u);
+}
+
+// ---------------------------------------------------------------------------------------- ETC1s
+// floor((a+b)/2) on four bytes at once
+GB_DEV uint32_t floor_avg4(uint32_t a, uint32_t b) { return (a & b) + (((a ^ b) & 0xFEFEFEFEu) >> 1); }
+
+// Output (goofy_tc.h:1358-1493): word0 = R5<<3 | G5<<11 | B5<<19 | control<<24;
+// word1 = ~(GezPlane | LqtPlane << 16), pixel (x,y) at plane bit ((x^2)<<2)+y.
+// `controlLut[range]` = control byte << 24 (the reference's table, goofy_tc.h:1040-1057).
+GB_DEV void encode_etc1(const uint32_t (&p)[16], const BlockFront& f, const uint32_t* controlLut, uint32_t& word0,
+                        uint32_t& word1)
+{
+    // Plane bit order is column major starting at column 2: low lane walks columns 2,3
+    // (plane bits 0..7), high lane columns 0,1 (plane bits 8..15).
+    uint32_t accNeg = 0, accFar = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int y = k & 3, x = k >> 2;
+        const uint32_t e = lanes_of(p[4 * y + 2 + x], p[4 * y + x], f.laneBias);
+        const uint32_t x2 = lqt_lanes(e, f);
+        accNeg = bitsel(~e, accNeg >> 1, 0x40004000u);   // !Gez
+        accFar = bitsel(~x2, accFar >> 1, 0x80008000u);  // !Lqt
+    }
+    // lanes hold their 8 flags at bits 7..14 (accNeg) and 8..15 (accFar)
+    word1 = prmt(accNeg >> 7, accFar >> 8, 0x6420);
+
+    // Average colour: the reference's fixed tree of rounded-UP averages (goofy_tc.h:1402-1414),
+    // evaluated on complemented bytes so each node is a floor average (3 ops).
+    uint32_t col[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const uint32_t top = floor_avg4(~p[x], ~p[4 + x]);
+        const uint32_t bot = floor_avg4(~p[8 + x], ~p[12 + x]);
+        col[x] = floor_avg4(top, bot);
+    }
+    const uint32_t avg = ~floor_avg4(floor_avg4(col[0], col[1]), floor_avg4(col[2], col[3]));
+
+    // Shift the average colour so its brightness becomes `mid` (goofy_tc.h:1431-1449):
+    // base = clamp(avg + d, 0, 255) per channel with d = clamp(mid - Y(avg), -127, 127).
+    const int avgY = (int)(dp4a(avg, kLuma, 3u) >> 2);
+    int d = (int)f.mid - avgY;
+    d = d < -127 ? -127 : d;
+    d = d > 127 ? 127 : d;
+    const uint32_t d2 = prmt((uint32_t)d, 0u, 0x1010);
+    const uint32_t rb = addclamp_s16x2(avg & 0x00FF00FFu, d2, 0x00FF00FFu);  // lanes (R, B)
+    int g = (int)((avg >> 8) & 0xFFu) + d;
+    g = g < 0 ? 0 : g;
+    g = g > 255 ? 255 : g;
+
+    // to5, already positioned: (max(v,1)-1) & 0xF8 is to5(v) << 3
+    const uint32_t rb5 = (max2_u16x2(rb, 0x00010001u) - 0x00010001u) & 0x00F800F8u;
+    const uint32_t g5 = (uint32_t)((g > 1 ? g : 1) - 1) & 0xF8u;
+    word0 = rb5 | (g5 << 8) | controlLut[f.range];
+}
+
+// The reference's table (goofy_tc.h:1040-1057) steps at 22,44,74,106,152,182,254 and holds
+// (cw<<5 | cw<<2 | 0b11) << 24: both sub-block tables equal, diff = 1, flip = 1.
+GB_DEV uint32_t etc1_control_word(uint32_t range)
+{
+    const uint32_t cw = (range >= 22u) + (range >= 44u) + (range >= 74u) + (range >= 106u) + (range >= 152u) +
+                        (range >= 182u) + (range >= 254u);
+    return (cw * 36u + 3u) << 24;
+}
+
+}  // namespace gb

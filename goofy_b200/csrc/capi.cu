@@ -1,0 +1,556 @@
+// capi.cu -- the extern "C" layer of libgoofy_b200.so (declared in include/goofy_b200.h).
+//
+// Thin by design: argument checks that mirror goofy::compressDXT1/ETC1
+// (GoofyTC/goofy_tc.h:1497-1557), launch configuration, the host-pointer staging pipeline and
+// the multi-GPU shard scheduler.  All arithmetic lives in block_codec.cuh.  There is no CPU
+// encoder anywhere in this library: without a CUDA device every call returns an error code.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/goofy_b200.h"
+#include "encode_kernels.cuh"
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? GOOFY_B200_OK : GOOFY_B200_E_CUDA_BASE - (int)e; }
+
+#define GB_CUDA(call)                                   \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cuda_rc(e__);    \
+    } while (0)
+
+// ---- per-device one-time state: the ETC1 control table in device memory ----
+constexpr int kMaxDevices = 64;
+std::once_flag g_lutOnce[kMaxDevices];
+int g_lutStatus[kMaxDevices];
+
+int ensure_device_ready(int* deviceOut = nullptr)
+{
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cudaGetLastError(); return GOOFY_B200_E_DEVICE; }
+    if (dev < 0 || dev >= kMaxDevices) return GOOFY_B200_E_DEVICE;
+    std::call_once(g_lutOnce[dev], [dev]() {
+        gb::fill_control_lut_kernel<<<1, 256>>>();
+        cudaError_t le = cudaGetLastError();
+        if (le == cudaSuccess) le = cudaDeviceSynchronize();
+        g_lutStatus[dev] = cuda_rc(le);
+    });
+    if (deviceOut) *deviceOut = dev;
+    return g_lutStatus[dev];
+}
+
+// Shape checks in the reference's order (goofy_tc.h:1500-1508), then the new ones.
+int check_shape(uint32_t width, uint32_t height, uint32_t stride)
+{
+    if (width % 16u != 0u) return GOOFY_B200_E_WIDTH;
+    if (height % 4u != 0u) return GOOFY_B200_E_HEIGHT;
+    if (width == 0u || height == 0u) return GOOFY_B200_OK;
+    if ((uint64_t)stride < (uint64_t)width * 4u) return GOOFY_B200_E_STRIDE;
+    if (stride % 16u != 0u) return GOOFY_B200_E_ALIGN;
+    return GOOFY_B200_OK;
+}
+
+int check_pointers(const void* src, const void* dst)
+{
+    if (!src || !dst) return GOOFY_B200_E_NULL;
+    if (((uintptr_t)src & 15u) != 0u || ((uintptr_t)dst & 7u) != 0u) return GOOFY_B200_E_ALIGN;
+    return GOOFY_B200_OK;
+}
+
+template <int MODE>
+int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream)
+{
+    // threads: x walks blocks along a row (coalescing), y stacks block rows for narrow images
+    // (x is a power of two and x*y == 256: the kernels rely on exactly 256 threads)
+    uint32_t tx = 32u;
+    while (tx < 256u && tx < P.bw) tx <<= 1;
+    const uint32_t ty = 256u / tx;
+    const dim3 block(tx, ty, 1);
+    const uint32_t gx = (P.bw + tx - 1u) / tx;
+    const uint32_t rowsPerLaunch = 65535u * ty;
+    for (uint32_t img0 = 0; img0 < nImages; img0 += 65535u) {
+        const uint32_t nz = nImages - img0 < 65535u ? nImages - img0 : 65535u;
+        for (uint32_t by0 = 0; by0 < P.bh; by0 += rowsPerLaunch) {
+            const uint32_t rows = P.bh - by0 < rowsPerLaunch ? P.bh - by0 : rowsPerLaunch;
+            gb::EncodeParams Q = P;
+            Q.by0 = by0;
+            Q.src += (uint64_t)img0 * P.srcPitch;
+            Q.dst += (uint64_t)img0 * P.dstPitch;
+            if (Q.dst2) Q.dst2 += (uint64_t)img0 * P.dstPitch;
+            const dim3 grid(gx, (rows + ty - 1u) / ty, nz);
+            gb::encode_direct_kernel<MODE><<<grid, block, 0, stream>>>(Q);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            GB_CUDA(cudaGetLastError());
+        }
+    }
+    return GOOFY_B200_OK;
+}
+
+int encode_uniform(int mode, void* dst, void* dst2, const void* src, uint32_t width, uint32_t height, uint32_t stride,
+                   uint64_t srcPitch, uint64_t dstPitch, uint32_t nImages, cudaStream_t stream)
+{
+    int rc = check_shape(width, height, stride);
+    if (rc != GOOFY_B200_OK) return rc;
+    if (width == 0u || height == 0u || nImages == 0u) return GOOFY_B200_OK;
+    rc = check_pointers(src, dst);
+    if (rc != GOOFY_B200_OK) return rc;
+    if (mode == gb::kDual) {
+        rc = check_pointers(src, dst2);
+        if (rc != GOOFY_B200_OK) return rc;
+    }
+    if (nImages > 1u && ((srcPitch & 15u) != 0u || (dstPitch & 7u) != 0u)) return GOOFY_B200_E_ALIGN;
+    rc = ensure_device_ready();
+    if (rc != GOOFY_B200_OK) return rc;
+
+    gb::EncodeParams P;
+    P.src = (const uint8_t*)src;
+    P.dst = (uint8_t*)dst;
+    P.dst2 = (uint8_t*)dst2;
+    P.bw = width / 4u;
+    P.bh = height / 4u;
+    P.stride = stride;
+    P.by0 = 0;
+    P.srcPitch = srcPitch;
+    P.dstPitch = dstPitch;
+    switch (mode) {
+        case gb::kDxt1: return launch_direct<gb::kDxt1>(P, nImages, stream);
+        case gb::kEtc1: return launch_direct<gb::kEtc1>(P, nImages, stream);
+        case gb::kDual: return launch_direct<gb::kDual>(P, nImages, stream);
+        default: return GOOFY_B200_E_CODEC;
+    }
+}
+
+// ---------------------------------------------------------------- host-pointer pipeline
+// The image is cut into strips of whole block rows; strip i runs H2D -> kernel -> D2H on
+// stream i % kSlots so the copies of neighbouring strips overlap each other and the kernels.
+// Device scratch is cached per host thread and device and only ever grows.
+constexpr int kSlots = 3;
+constexpr size_t kStripBytes = 16u << 20;
+
+struct HostPipe {
+    int device = -1;
+    cudaStream_t stream[kSlots] = {};
+    void* dIn[kSlots] = {};
+    void* dOut[kSlots] = {};
+    size_t capIn = 0, capOut = 0;
+    bool ready = false;
+
+    int prepare(int dev, size_t needIn, size_t needOut)
+    {
+        if (ready && dev != device) release();
+        if (!ready) {
+            for (int i = 0; i < kSlots; ++i) GB_CUDA(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
+            device = dev;
+            ready = true;
+        }
+        if (needIn > capIn) {
+            for (int i = 0; i < kSlots; ++i) {
+                if (dIn[i]) cudaFree(dIn[i]);
+                dIn[i] = nullptr;
+                GB_CUDA(cudaMalloc(&dIn[i], needIn));
+            }
+            capIn = needIn;
+        }
+        if (needOut > capOut) {
+            for (int i = 0; i < kSlots; ++i) {
+                if (dOut[i]) cudaFree(dOut[i]);
+                dOut[i] = nullptr;
+                GB_CUDA(cudaMalloc(&dOut[i], needOut));
+            }
+            capOut = needOut;
+        }
+        return GOOFY_B200_OK;
+    }
+    void release()
+    {
+        for (int i = 0; i < kSlots; ++i) {
+            if (dIn[i]) cudaFree(dIn[i]);
+            if (dOut[i]) cudaFree(dOut[i]);
+            if (stream[i]) cudaStreamDestroy(stream[i]);
+            dIn[i] = dOut[i] = nullptr;
+            stream[i] = nullptr;
+        }
+        capIn = capOut = 0;
+        ready = false;
+    }
+    // No destructor on purpose: thread_local teardown can run after the CUDA runtime has
+    // shut down; the driver reclaims everything at process exit.
+};
+
+thread_local HostPipe t_pipe;
+
+int encode_host(int codec, void* result, const void* input, uint32_t width, uint32_t height, uint32_t stride)
+{
+    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
+    int rc = check_shape(width, height, stride);
+    if (rc != GOOFY_B200_OK) return rc;
+    if (width == 0u || height == 0u) return GOOFY_B200_OK;
+    if (!result || !input) return GOOFY_B200_E_NULL;
+    if (((uintptr_t)input & 15u) != 0u) return GOOFY_B200_E_ALIGN;  // the reference's aligned-load contract
+    int dev = -1;
+    rc = ensure_device_ready(&dev);
+    if (rc != GOOFY_B200_OK) return rc;
+
+    const size_t rowBytes = (size_t)width * 4u;
+    const uint32_t blockRows = height / 4u;
+    uint32_t stripRows = (uint32_t)(kStripBytes / (rowBytes * 4u));
+    if (stripRows == 0u) stripRows = 1u;
+    if (stripRows > blockRows) stripRows = blockRows;
+    const size_t outRowBytes = (size_t)(width / 4u) * 8u;
+    rc = t_pipe.prepare(dev, (size_t)stripRows * 4u * rowBytes, (size_t)stripRows * outRowBytes);
+    if (rc != GOOFY_B200_OK) return rc;
+
+    int slot = 0;
+    for (uint32_t r0 = 0; r0 < blockRows; r0 += stripRows, slot = (slot + 1) % kSlots) {
+        const uint32_t rows = blockRows - r0 < stripRows ? blockRows - r0 : stripRows;
+        cudaStream_t s = t_pipe.stream[slot];
+        // stream order protects the slot's scratch: its previous strip finished D2H on the same stream
+        GB_CUDA(cudaMemcpy2DAsync(t_pipe.dIn[slot], rowBytes, (const uint8_t*)input + (size_t)r0 * 4u * stride, stride,
+                                  rowBytes, (size_t)rows * 4u, cudaMemcpyHostToDevice, s));
+        rc = encode_uniform(codec, t_pipe.dOut[slot], nullptr, t_pipe.dIn[slot], width, rows * 4u, (uint32_t)rowBytes, 0, 0,
+                            1, s);
+        if (rc != GOOFY_B200_OK) return rc;
+        GB_CUDA(cudaMemcpyAsync((uint8_t*)result + (size_t)r0 * outRowBytes, t_pipe.dOut[slot], (size_t)rows * outRowBytes,
+                                cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < kSlots; ++i) GB_CUDA(cudaStreamSynchronize(t_pipe.stream[i]));
+    return GOOFY_B200_OK;
+}
+
+// ---------------------------------------------------------------- ragged batch
+template <int MODE>
+int launch_batch(const gb::BatchImage* dImages, const uint32_t* dStart, uint32_t n, uint32_t totalCtas, cudaStream_t stream)
+{
+    gb::encode_batch_kernel<MODE><<<totalCtas, dim3(gb::kBatchTileX, gb::kBatchTileY, 1), 0, stream>>>(dImages, dStart, n);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
+// Descriptor tables live in a small per-thread device arena that is recycled in stream order.
+struct BatchArena {
+    void* dev = nullptr;
+    void* host = nullptr;  // pinned
+    size_t cap = 0;
+    int device = -1;
+    cudaEvent_t done = nullptr;
+};
+thread_local BatchArena t_arena;
+
+int encode_batch_current_device(int codec, const GoofyB200Image* descs, const uint32_t* order, uint32_t n, cudaStream_t stream)
+{
+    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
+    if (n == 0u) return GOOFY_B200_OK;
+    if (!descs) return GOOFY_B200_E_NULL;
+    int dev = -1;
+    int rc = ensure_device_ready(&dev);
+    if (rc != GOOFY_B200_OK) return rc;
+
+    std::vector<gb::BatchImage> images;
+    std::vector<uint32_t> start;
+    images.reserve(n);
+    start.reserve(n + 1);
+    uint64_t total = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const GoofyB200Image& d = descs[order ? order[k] : k];
+        rc = check_shape(d.width, d.height, d.stride);
+        if (rc != GOOFY_B200_OK) return rc;
+        if (d.width == 0u || d.height == 0u) continue;
+        rc = check_pointers(d.src, d.dst);
+        if (rc != GOOFY_B200_OK) return rc;
+        gb::BatchImage im;
+        im.src = (const uint8_t*)d.src;
+        im.dst = (uint8_t*)d.dst;
+        im.bw = d.width / 4u;
+        im.bh = d.height / 4u;
+        im.stride = d.stride;
+        im.tilesX = (im.bw + gb::kBatchTileX - 1u) / gb::kBatchTileX;
+        start.push_back((uint32_t)total);
+        total += (uint64_t)im.tilesX * ((im.bh + gb::kBatchTileY - 1u) / gb::kBatchTileY);
+        if (total > 0x7FFFFFFFull) return GOOFY_B200_E_ARGS;
+        images.push_back(im);
+    }
+    if (images.empty()) return GOOFY_B200_OK;
+    const uint32_t m = (uint32_t)images.size();
+    const size_t bytesImages = (size_t)m * sizeof(gb::BatchImage);
+    const size_t bytes = bytesImages + (size_t)m * sizeof(uint32_t);
+
+    BatchArena& A = t_arena;
+    if (A.device != dev || bytes > A.cap) {
+        if (A.done) { cudaEventSynchronize(A.done); }
+        if (A.dev) cudaFree(A.dev);
+        if (A.host) cudaFreeHost(A.host);
+        A.dev = A.host = nullptr;
+        A.cap = 0;
+        size_t cap = bytes < (1u << 16) ? (1u << 16) : bytes * 2u;
+        GB_CUDA(cudaMalloc(&A.dev, cap));
+        GB_CUDA(cudaHostAlloc(&A.host, cap, cudaHostAllocDefault));
+        if (!A.done) GB_CUDA(cudaEventCreateWithFlags(&A.done, cudaEventDisableTiming));
+        A.cap = cap;
+        A.device = dev;
+    } else if (A.done) {
+        GB_CUDA(cudaEventSynchronize(A.done));  // previous batch has consumed the table
+    }
+    std::memcpy(A.host, images.data(), bytesImages);
+    std::memcpy((uint8_t*)A.host + bytesImages, start.data(), (size_t)m * sizeof(uint32_t));
+    GB_CUDA(cudaMemcpyAsync(A.dev, A.host, bytes, cudaMemcpyHostToDevice, stream));
+    const gb::BatchImage* dImages = (const gb::BatchImage*)A.dev;
+    const uint32_t* dStart = (const uint32_t*)((const uint8_t*)A.dev + bytesImages);
+    rc = codec == GOOFY_B200_DXT1 ? launch_batch<gb::kDxt1>(dImages, dStart, m, (uint32_t)total, stream)
+                                  : launch_batch<gb::kEtc1>(dImages, dStart, m, (uint32_t)total, stream);
+    if (rc != GOOFY_B200_OK) return rc;
+    GB_CUDA(cudaEventRecord(A.done, stream));
+    return GOOFY_B200_OK;
+}
+
+// ---------------------------------------------------------------- shard scheduler
+// One persistent host thread per device.  A job is a closure run with that device current;
+// there is no cross-device communication of any kind (blocks are independent).
+class DeviceWorker {
+public:
+    explicit DeviceWorker(int device) : device_(device), thread_([this] { loop(); }) {}
+    ~DeviceWorker()
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        thread_.join();
+    }
+    void submit(std::function<int()> job)
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            job_ = std::move(job);
+            hasJob_ = true;
+            done_ = false;
+        }
+        cv_.notify_all();
+    }
+    int wait()
+    {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [this] { return done_; });
+        return rc_;
+    }
+
+private:
+    void loop()
+    {
+        cudaSetDevice(device_);
+        for (;;) {
+            std::function<int()> job;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [this] { return hasJob_ || stop_; });
+                if (stop_) return;
+                job = std::move(job_);
+                hasJob_ = false;
+            }
+            const int rc = job();
+            {
+                std::lock_guard<std::mutex> g(m_);
+                rc_ = rc;
+                done_ = true;
+            }
+            cv_.notify_all();
+        }
+    }
+    int device_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::function<int()> job_;
+    bool hasJob_ = false, done_ = true, stop_ = false;
+    int rc_ = 0;
+    std::thread thread_;
+};
+
+std::mutex g_schedMutex;  // one sharded call at a time per process
+std::vector<DeviceWorker*> g_workers;  // leaked at exit on purpose (see HostPipe)
+
+int device_count()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+DeviceWorker* worker_for(int device)
+{
+    if ((int)g_workers.size() <= device) g_workers.resize((size_t)device + 1, nullptr);
+    if (!g_workers[(size_t)device]) g_workers[(size_t)device] = new DeviceWorker(device);
+    return g_workers[(size_t)device];
+}
+
+}  // namespace
+
+// ======================================================================== extern "C"
+extern "C" {
+
+int goofy_b200_abi_version(void) { return GOOFY_B200_ABI_VERSION; }
+
+int goofy_b200_device_count(void) { return device_count(); }
+
+uint64_t goofy_b200_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* goofy_b200_error_string(int code)
+{
+    switch (code) {
+        case GOOFY_B200_OK: return "ok";
+        case GOOFY_B200_E_WIDTH: return "width is not a multiple of 16";
+        case GOOFY_B200_E_HEIGHT: return "height is not a multiple of 4";
+        case GOOFY_B200_E_NULL: return "null pointer";
+        case GOOFY_B200_E_ALIGN: return "input/stride must be 16-byte aligned, output 8-byte aligned";
+        case GOOFY_B200_E_STRIDE: return "stride smaller than width*4";
+        case GOOFY_B200_E_CODEC: return "unknown codec";
+        case GOOFY_B200_E_DEVICE: return "no usable CUDA device";
+        case GOOFY_B200_E_ARGS: return "invalid argument";
+        default: break;
+    }
+    if (code <= GOOFY_B200_E_CUDA_BASE) return cudaGetErrorString((cudaError_t)(GOOFY_B200_E_CUDA_BASE - code));
+    return "unknown error";
+}
+
+int goofy_b200_compress_dxt1(unsigned char* result, const unsigned char* input, unsigned int width, unsigned int height,
+                             unsigned int stride)
+{
+    return encode_host(GOOFY_B200_DXT1, result, input, width, height, stride);
+}
+
+int goofy_b200_compress_etc1(unsigned char* result, const unsigned char* input, unsigned int width, unsigned int height,
+                             unsigned int stride)
+{
+    return encode_host(GOOFY_B200_ETC1, result, input, width, height, stride);
+}
+
+int goofy_b200_encode_host(int codec, void* result, const void* input, uint32_t width, uint32_t height, uint32_t stride)
+{
+    return encode_host(codec, result, input, width, height, stride);
+}
+
+int goofy_b200_encode_device(int codec, void* d_result, const void* d_input, uint32_t width, uint32_t height,
+                             uint32_t stride, void* stream)
+{
+    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
+    return encode_uniform(codec, d_result, nullptr, d_input, width, height, stride, 0, 0, 1, (cudaStream_t)stream);
+}
+
+int goofy_b200_encode_batch_uniform_device(int codec, void* d_result, const void* d_input, uint32_t width, uint32_t height,
+                                           uint32_t stride, uint64_t input_image_pitch, uint64_t result_image_pitch,
+                                           uint32_t n_images, void* stream)
+{
+    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
+    return encode_uniform(codec, d_result, nullptr, d_input, width, height, stride, input_image_pitch, result_image_pitch,
+                          n_images, (cudaStream_t)stream);
+}
+
+int goofy_b200_encode_dual_device(void* d_result_dxt1, void* d_result_etc1, const void* d_input, uint32_t width,
+                                  uint32_t height, uint32_t stride, uint64_t input_image_pitch, uint64_t result_image_pitch,
+                                  uint32_t n_images, void* stream)
+{
+    return encode_uniform(gb::kDual, d_result_dxt1, d_result_etc1, d_input, width, height, stride, input_image_pitch,
+                          result_image_pitch, n_images, (cudaStream_t)stream);
+}
+
+int goofy_b200_encode_batch_device(int codec, const GoofyB200Image* descs, uint32_t n_images, void* stream)
+{
+    if (n_images && descs) {
+        int dev = -1;
+        if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return GOOFY_B200_E_DEVICE; }
+        for (uint32_t i = 0; i < n_images; ++i)
+            if (descs[i].device >= 0 && descs[i].device != dev) return GOOFY_B200_E_DEVICE;
+    }
+    return encode_batch_current_device(codec, descs, nullptr, n_images, (cudaStream_t)stream);
+}
+
+int goofy_b200_encode_batch_sharded(int codec, const GoofyB200Image* descs, uint32_t n_images)
+{
+    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
+    if (n_images == 0u) return GOOFY_B200_OK;
+    if (!descs) return GOOFY_B200_E_NULL;
+    const int nDev = device_count();
+    if (nDev <= 0) return GOOFY_B200_E_DEVICE;
+    std::vector<std::vector<uint32_t>> perDevice((size_t)nDev);
+    for (uint32_t i = 0; i < n_images; ++i) {
+        if (descs[i].device < 0 || descs[i].device >= nDev) return GOOFY_B200_E_DEVICE;
+        perDevice[(size_t)descs[i].device].push_back(i);
+    }
+    std::lock_guard<std::mutex> lock(g_schedMutex);
+    std::vector<int> used;
+    for (int d = 0; d < nDev; ++d) {
+        if (perDevice[(size_t)d].empty()) continue;
+        const std::vector<uint32_t>* order = &perDevice[(size_t)d];
+        worker_for(d)->submit([codec, descs, order]() {
+            int rc = encode_batch_current_device(codec, descs, order->data(), (uint32_t)order->size(), nullptr);
+            if (rc != GOOFY_B200_OK) return rc;
+            return cuda_rc(cudaStreamSynchronize(nullptr));
+        });
+        used.push_back(d);
+    }
+    int rc = GOOFY_B200_OK;
+    for (int d : used) {
+        const int r = g_workers[(size_t)d]->wait();
+        if (r != GOOFY_B200_OK && rc == GOOFY_B200_OK) rc = r;
+    }
+    return rc;
+}
+
+void goofy_b200_strip_partition(uint32_t height, int n_shards, int shard, uint32_t* first_block_row,
+                                uint32_t* block_row_count)
+{
+    const uint32_t rows = height / 4u;
+    uint32_t first = 0, count = 0;
+    if (n_shards > 0 && shard >= 0 && shard < n_shards) {
+        first = (uint32_t)((uint64_t)rows * (uint32_t)shard / (uint32_t)n_shards);
+        const uint32_t next = (uint32_t)((uint64_t)rows * ((uint32_t)shard + 1u) / (uint32_t)n_shards);
+        count = next - first;
+    }
+    if (first_block_row) *first_block_row = first;
+    if (block_row_count) *block_row_count = count;
+}
+
+int goofy_b200_encode_sharded_host(int codec, void* result, const void* input, uint32_t width, uint32_t height,
+                                   uint32_t stride, int n_gpus)
+{
+    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
+    int rc = check_shape(width, height, stride);
+    if (rc != GOOFY_B200_OK) return rc;
+    if (width == 0u || height == 0u) return GOOFY_B200_OK;
+    if (!result || !input) return GOOFY_B200_E_NULL;
+    const int nDev = device_count();
+    if (nDev <= 0) return GOOFY_B200_E_DEVICE;
+    if (n_gpus <= 0) n_gpus = nDev;
+    if (n_gpus > nDev) return GOOFY_B200_E_DEVICE;
+
+    std::lock_guard<std::mutex> lock(g_schedMutex);
+    std::vector<int> used;
+    for (int g = 0; g < n_gpus; ++g) {
+        uint32_t first = 0, count = 0;
+        goofy_b200_strip_partition(height, n_gpus, g, &first, &count);
+        if (count == 0u) continue;
+        uint8_t* out = (uint8_t*)result + (size_t)first * (width / 4u) * 8u;
+        const uint8_t* in = (const uint8_t*)input + (size_t)first * 4u * stride;
+        worker_for(g)->submit([=]() { return encode_host(codec, out, in, width, count * 4u, stride); });
+        used.push_back(g);
+    }
+    for (int g : used) {
+        const int r = g_workers[(size_t)g]->wait();
+        if (r != GOOFY_B200_OK && rc == GOOFY_B200_OK) rc = r;
+    }
+    return rc;
+}
+
+}  // extern "C"

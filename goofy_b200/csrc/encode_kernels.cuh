@@ -1,0 +1,143 @@
+// encode_kernels.cuh -- the global kernels around block_codec.cuh: image load/tiling layer
+// and output block writer.
+//
+// Replaces the row/tile loops of goofy::compressDXT1/ETC1 (GoofyTC/goofy_tc.h:1514-1524,
+// :1545-1555) and the tile fetch / dword stores of goofySimdEncode (:1077-1099, :1332-1356,
+// :1476-1492).  One thread owns one 4x4 block:
+//   load   4 x LDG.128 (one per block row).  A warp covers 32 adjacent blocks, so each of the
+//          four requests is 512 contiguous bytes -- four full 128-byte lines, fully coalesced.
+//   store  one 8-byte block per thread -> 256 contiguous bytes per warp.
+// Inputs are streamed once, so loads bypass L1 allocation and stores are streaming.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "block_codec.cuh"
+
+namespace gb {
+
+enum Mode : int { kDxt1 = 0, kEtc1 = 1, kDual = 2 };
+
+struct EncodeParams {
+    const uint8_t* src;
+    uint8_t* dst;        // DXT1 (kDxt1, kDual) or ETC1 (kEtc1) blocks
+    uint8_t* dst2;       // ETC1 blocks for kDual
+    uint32_t bw, bh;     // image size in blocks
+    uint32_t stride;     // bytes between pixel rows
+    uint32_t by0;        // first block row handled by this launch (grid.y chunking)
+    uint64_t srcPitch;   // bytes between images
+    uint64_t dstPitch;
+};
+
+// ETC1 control words by clamped brightness range; filled once per device by the host
+// (same content as the reference's table, goofy_tc.h:1040-1057, generated not copied).
+__device__ uint32_t g_etc1ControlLut[256];
+
+__global__ void fill_control_lut_kernel()
+{
+    g_etc1ControlLut[threadIdx.x] = etc1_control_word(threadIdx.x);
+}
+
+__device__ __forceinline__ uint4 load_row(const uint8_t* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void store_block(uint8_t* p, uint32_t w0, uint32_t w1)
+{
+    asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(w0), "r"(w1) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) encode_direct_kernel(const EncodeParams P)
+{
+    __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
+    if (MODE != kDxt1) {
+        // the launcher always uses 256 threads (x a power of two, x*y == 256)
+        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
+        lut[t] = g_etc1ControlLut[t];
+        __syncthreads();
+    }
+
+    const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t by = P.by0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (bx >= P.bw || by >= P.bh) return;
+
+    const uint8_t* s = P.src + (uint64_t)blockIdx.z * P.srcPitch + (uint64_t)by * 4u * P.stride + (uint64_t)bx * 16u;
+    const uint4 r0 = load_row(s);
+    const uint4 r1 = load_row(s + P.stride);
+    const uint4 r2 = load_row(s + 2ull * P.stride);
+    const uint4 r3 = load_row(s + 3ull * P.stride);
+    const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
+                            r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+
+    const uint64_t o = (uint64_t)blockIdx.z * P.dstPitch + ((uint64_t)by * P.bw + bx) * 8u;
+    const BlockFront f = analyse(p);
+    uint32_t w0, w1;
+    if (MODE == kDxt1 || MODE == kDual) {
+        encode_dxt1(p, f, w0, w1);
+        store_block(P.dst + o, w0, w1);
+    }
+    if (MODE == kEtc1 || MODE == kDual) {
+        encode_etc1(p, f, lut, w0, w1);
+        store_block((MODE == kDual ? P.dst2 : P.dst) + o, w0, w1);
+    }
+}
+
+// ------------------------------------------------------------------ ragged batches
+// Images of different shapes in one launch.  The host sorts nothing: it uploads the
+// descriptors plus an exclusive prefix sum of per-image CTA counts; each CTA finds its
+// image by binary search and its tile by one division.
+struct BatchImage {
+    const uint8_t* src;
+    uint8_t* dst;
+    uint32_t bw, bh;
+    uint32_t stride;
+    uint32_t tilesX;  // CTAs per block row
+};
+
+constexpr int kBatchTileX = 64;  // blocks per CTA in x
+constexpr int kBatchTileY = 4;   // block rows per CTA
+
+template <int MODE>
+__global__ void __launch_bounds__(kBatchTileX* kBatchTileY)
+    encode_batch_kernel(const BatchImage* __restrict__ images, const uint32_t* __restrict__ ctaStart, uint32_t nImages)
+{
+    __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
+    if (MODE != kDxt1) {
+        const uint32_t t = threadIdx.y * kBatchTileX + threadIdx.x;
+        lut[t] = g_etc1ControlLut[t];
+        __syncthreads();
+    }
+    // largest i with ctaStart[i] <= blockIdx.x
+    uint32_t lo = 0, hi = nImages;
+    while (hi - lo > 1u) {
+        const uint32_t m = (lo + hi) >> 1;
+        if (ctaStart[m] <= blockIdx.x) lo = m; else hi = m;
+    }
+    const BatchImage im = images[lo];
+    const uint32_t local = blockIdx.x - ctaStart[lo];
+    const uint32_t ty = local / im.tilesX, tx = local - ty * im.tilesX;
+    const uint32_t bx = tx * kBatchTileX + threadIdx.x;
+    const uint32_t by = ty * kBatchTileY + threadIdx.y;
+    if (bx >= im.bw || by >= im.bh) return;
+
+    const uint8_t* s = im.src + (uint64_t)by * 4u * im.stride + (uint64_t)bx * 16u;
+    const uint4 r0 = load_row(s);
+    const uint4 r1 = load_row(s + im.stride);
+    const uint4 r2 = load_row(s + 2ull * im.stride);
+    const uint4 r3 = load_row(s + 3ull * im.stride);
+    const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
+                            r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+    const BlockFront f = analyse(p);
+    uint32_t w0, w1;
+    if (MODE == kDxt1) encode_dxt1(p, f, w0, w1);
+    else encode_etc1(p, f, lut, w0, w1);
+    store_block(im.dst + ((uint64_t)by * im.bw + bx) * 8u, w0, w1);
+}
+
+}  // namespace gb

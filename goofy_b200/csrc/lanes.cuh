@@ -1,0 +1,87 @@
+// lanes.cuh -- the handful of packed-integer primitives the block encoders are built from.
+//
+// On the device every one of these is a single sm_100a instruction (checked with
+// cuobjdump -sass, see DESIGN.md "instruction budget"):
+//   dp4a        IDP.4A.U8.U8      4 x (u8*u8) + u32
+//   prmt        PRMT              byte permute of two words
+//   min3/max3   VIMNMX3.U16x2     3-input min/max on two u16 lanes
+//   min2/max2   VIMNMX.U16x2
+//   bitsel      LOP3.LUT          (a & m) | (b & ~m)
+// These stand in for the SSE2 pminub/pmaxub/pavgb/punpck*/pmovmskb sequences of the
+// reference (GoofyTC/goofy_tc.h:170-396); the encoders do NOT transliterate those ops,
+// they use closed forms on u16x2 lanes.
+//
+// GOOFY_B200_HOST_EMULATION is defined ONLY by tests/kernel_math_host.cpp, which compiles
+// block_codec.cuh with g++ to check the kernel arithmetic against the oracle on a machine
+// without a GPU.  The product library is always built by nvcc and never takes that branch.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GB_DEV __device__ __forceinline__
+#else
+#ifndef GOOFY_B200_HOST_EMULATION
+#error "lanes.cuh: device code only (host emulation exists for tests/kernel_math_host.cpp alone)"
+#endif
+#define GB_DEV static inline
+#endif
+
+namespace gb {
+
+#if defined(__CUDACC__)
+
+GB_DEV uint32_t dp4a(uint32_t a, uint32_t w, uint32_t c) { return __dp4a(a, w, c); }
+GB_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+GB_DEV uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+GB_DEV uint32_t max3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+GB_DEV uint32_t min2_u16x2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+GB_DEV uint32_t max2_u16x2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+// per-lane clamp(a + b, 0, c) on two signed 16-bit lanes
+GB_DEV uint32_t addclamp_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2_relu(a, b, c); }
+
+#else  // host emulation (tests only)
+
+GB_DEV uint32_t dp4a(uint32_t a, uint32_t w, uint32_t c)
+{
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 255u) * ((w >> (8 * i)) & 255u);
+    return c;
+}
+GB_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 255u) << (8 * i);
+    return r;
+}
+GB_DEV uint32_t lanes_(uint32_t lo, uint32_t hi) { return (lo & 0xFFFFu) | (hi << 16); }
+GB_DEV uint32_t min2_u16x2(uint32_t a, uint32_t b)
+{
+    uint32_t al = a & 0xFFFFu, bl = b & 0xFFFFu, ah = a >> 16, bh = b >> 16;
+    return lanes_(al < bl ? al : bl, ah < bh ? ah : bh);
+}
+GB_DEV uint32_t max2_u16x2(uint32_t a, uint32_t b)
+{
+    uint32_t al = a & 0xFFFFu, bl = b & 0xFFFFu, ah = a >> 16, bh = b >> 16;
+    return lanes_(al > bl ? al : bl, ah > bh ? ah : bh);
+}
+GB_DEV uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return min2_u16x2(min2_u16x2(a, b), c); }
+GB_DEV uint32_t max3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return max2_u16x2(max2_u16x2(a, b), c); }
+GB_DEV uint32_t addclamp_s16x2(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 2; ++i) {
+        int v = (int)(int16_t)(a >> (16 * i)) + (int)(int16_t)(b >> (16 * i));
+        int hi = (int)(int16_t)(c >> (16 * i));
+        if (v > hi) v = hi;
+        if (v < 0) v = 0;
+        r |= ((uint32_t)v & 0xFFFFu) << (16 * i);
+    }
+    return r;
+}
+
+#endif
+
+// (a & m) | (b & ~m): one LOP3
+GB_DEV uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
+
+}  // namespace gb

@@ -1,0 +1,119 @@
+/*
+ * goofy_b200.h -- C ABI of libgoofy_b200.so, the B200 (sm_100a) implementation of Goofy's
+ * DXT1/BC1 and ETC1s block encoders.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  The C++
+ * wrappers in include/goofy_tc.h (namespace goofy, same signatures as the reference) and
+ * the Python mirror in goofy_b200/api.py both sit on top of exactly these entry points.
+ * There is NO CPU fallback: every entry point returns a GOOFY_B200_E_* code if CUDA or a
+ * B200-class device is unavailable.
+ *
+ * Reference interface each entry point replaces (paths into the reference repository):
+ *   goofy_b200_compress_dxt1  <- goofy::compressDXT1   GoofyTC/goofy_tc.h:11, defined :1497-1526
+ *   goofy_b200_compress_etc1  <- goofy::compressETC1   GoofyTC/goofy_tc.h:12, defined :1528-1557
+ *   (function-pointer shape)  <- CompressFunc_t         Src/main.cpp:644
+ * The *_device / *_batch / *_dual / *_sharded entry points are the batched device-resident
+ * variants BASELINE.json's north_star adds; the per-block arithmetic they run is the same
+ * (goofySimdEncode<>, GoofyTC/goofy_tc.h:1069-1494).
+ *
+ * Image contract (identical to the reference, GoofyTC/goofy_tc.h:1497-1523 and :175-178):
+ *   - input is RGBA8, `stride` bytes between rows (may exceed width*4), alpha ignored;
+ *   - width % 16 == 0 (else -1), height % 4 == 0 (else -2), checked in that order;
+ *   - rows 16-byte aligned: input % 16 == 0 and stride % 16 == 0;
+ *   - output is (height/4)*(width/4) blocks of 8 bytes, row-major, width*height/2 bytes;
+ *   - width == 0 or height == 0 returns 0 and writes nothing.
+ */
+#ifndef GOOFY_B200_H
+#define GOOFY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOOFY_B200_ABI_VERSION 1
+
+/* codec selectors */
+#define GOOFY_B200_DXT1 0
+#define GOOFY_B200_ETC1 1
+
+/* return codes: 0, -1, -2 are the reference's; the rest are new and never collide with them */
+#define GOOFY_B200_OK 0
+#define GOOFY_B200_E_WIDTH (-1)      /* width % 16 != 0            (goofy_tc.h:1500-1503) */
+#define GOOFY_B200_E_HEIGHT (-2)     /* height % 4 != 0            (goofy_tc.h:1505-1508) */
+#define GOOFY_B200_E_NULL (-3)       /* null pointer with non-empty image */
+#define GOOFY_B200_E_ALIGN (-4)      /* input/stride not 16-byte, output not 8-byte aligned */
+#define GOOFY_B200_E_STRIDE (-5)     /* stride < width*4 */
+#define GOOFY_B200_E_CODEC (-6)      /* unknown codec selector */
+#define GOOFY_B200_E_DEVICE (-7)     /* no CUDA device / bad device index / wrong device for pointer */
+#define GOOFY_B200_E_ARGS (-8)       /* other invalid argument (batch size, pitch, ...) */
+#define GOOFY_B200_E_CUDA_BASE (-100) /* CUDA failure: code = -100 - cudaError_t */
+
+/* One image of a batch.  All pointers are device pointers on `device`
+ * (device < 0: the calling thread's current device). */
+typedef struct GoofyB200Image {
+    const void* src; /* RGBA8, 16-byte aligned */
+    void* dst;       /* width*height/2 bytes, 8-byte aligned */
+    uint32_t width;
+    uint32_t height;
+    uint32_t stride; /* bytes */
+    int32_t device;
+} GoofyB200Image;
+
+int goofy_b200_abi_version(void);
+int goofy_b200_device_count(void);
+/* Static description of a return code (never NULL). */
+const char* goofy_b200_error_string(int code);
+/* Kernels launched by this library in the calling process so far (all threads, all devices). */
+uint64_t goofy_b200_kernel_launches(void);
+
+/* ---- drop-in host-pointer API: same arguments, order and return codes as the reference ---- */
+int goofy_b200_compress_dxt1(unsigned char* result, const unsigned char* input, unsigned int width,
+                             unsigned int height, unsigned int stride);
+int goofy_b200_compress_etc1(unsigned char* result, const unsigned char* input, unsigned int width,
+                             unsigned int height, unsigned int stride);
+/* Same, codec chosen at run time.  Host buffers may be pageable or pinned; pinned buffers
+ * (cudaHostAlloc / cudaHostRegister) are copied without a staging hop.  Uses the calling
+ * thread's current device and synchronises before returning. */
+int goofy_b200_encode_host(int codec, void* result, const void* input, uint32_t width, uint32_t height,
+                           uint32_t stride);
+
+/* ---- device-resident API: pointers are device memory on the current device; asynchronous
+ *      on `stream` (a cudaStream_t, NULL = default stream); no allocation, no sync ---- */
+int goofy_b200_encode_device(int codec, void* d_result, const void* d_input, uint32_t width, uint32_t height,
+                             uint32_t stride, void* stream);
+
+/* n images of one shape laid out at fixed pitches (bytes) from d_input / d_result. */
+int goofy_b200_encode_batch_uniform_device(int codec, void* d_result, const void* d_input, uint32_t width,
+                                           uint32_t height, uint32_t stride, uint64_t input_image_pitch,
+                                           uint64_t result_image_pitch, uint32_t n_images, void* stream);
+
+/* Both codecs from one read of the input (5 B/px instead of 9 B/px of HBM traffic). */
+int goofy_b200_encode_dual_device(void* d_result_dxt1, void* d_result_etc1, const void* d_input, uint32_t width,
+                                  uint32_t height, uint32_t stride, uint64_t input_image_pitch,
+                                  uint64_t result_image_pitch, uint32_t n_images, void* stream);
+
+/* n images of arbitrary shapes on the current device (descs is a HOST array; descs[i].device
+ * must be < 0 or the current device).  One launch per call; the descriptor table is copied
+ * to the device on `stream`. */
+int goofy_b200_encode_batch_device(int codec, const GoofyB200Image* descs, uint32_t n_images, void* stream);
+
+/* ---- multi-GPU shard scheduler (no collectives: blocks are independent) ---- */
+/* Images may live on different devices (descs[i].device >= 0 required).  Work is grouped per
+ * device, launched from one host thread per device, and all devices are synchronised
+ * before returning. */
+int goofy_b200_encode_batch_sharded(int codec, const GoofyB200Image* descs, uint32_t n_images);
+/* One host image split into n_gpus horizontal strips of whole block rows; strip g is
+ * encoded on device g through the host path.  n_gpus <= 0 means all visible devices. */
+int goofy_b200_encode_sharded_host(int codec, void* result, const void* input, uint32_t width, uint32_t height,
+                                   uint32_t stride, int n_gpus);
+/* Strip partition used by the scheduler: block rows [first, first+count) for shard `shard`. */
+void goofy_b200_strip_partition(uint32_t height, int n_shards, int shard, uint32_t* first_block_row,
+                                uint32_t* block_row_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOOFY_B200_H */

@@ -1,0 +1,32 @@
+// kernel_math_host.cpp -- TEST ONLY.  Compiles the CUDA block codec (goofy_b200/csrc/block_codec.cuh)
+// for the host with the device intrinsics emulated (lanes.cuh, GOOFY_B200_HOST_EMULATION), so the
+// kernel's closed-form arithmetic can be checked against the oracle on a machine without a GPU.
+// This is a checker for the kernel source, not a product path: nothing in goofy_b200/ builds or loads it.
+#define GOOFY_B200_HOST_EMULATION 1
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+#include "../goofy_b200/csrc/block_codec.cuh"
+
+extern "C" int kernel_math_compress(int codec, unsigned char* result, const unsigned char* input, unsigned width,
+                                    unsigned height, unsigned stride)
+{
+    if (width % 16) return -1;
+    if (height % 4) return -2;
+    uint32_t lut[256];
+    for (uint32_t r = 0; r < 256; ++r) lut[r] = gb::etc1_control_word(r);
+    for (unsigned by = 0; by < height / 4; ++by)
+        for (unsigned bx = 0; bx < width / 4; ++bx) {
+            uint32_t p[16];
+            for (int y = 0; y < 4; ++y) std::memcpy(&p[4 * y], input + (size_t)(4 * by + y) * stride + (size_t)bx * 16, 16);
+            uint32_t w0, w1;
+            const gb::BlockFront f = gb::analyse(p);
+            if (codec == 0) gb::encode_dxt1(p, f, w0, w1);
+            else gb::encode_etc1(p, f, lut, w0, w1);
+            std::memcpy(result, &w0, 4);
+            std::memcpy(result + 4, &w1, 4);
+            result += 8;
+        }
+    return 0;
+}

@@ -1,0 +1,239 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, must be bit-exact with the oracle
+(and with the unmodified reference where oracle/_ref is present).  Run with -m gpu on a B200."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import goofy_b200 as gb  # noqa: E402
+from oracle.oracle import (DXT1, ETC1, aligned_copy, load_test_image, splitmix_rgba, synth_family,  # noqa: E402
+                           test_image_names)
+
+CODECS = [DXT1, ETC1]
+HOST_FN = {DXT1: gb.compressDXT1, ETC1: gb.compressETC1}
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_device(codec, img, w, h, stride=None):
+    stride = w * 4 if stride is None else stride
+    d_src = dev(np.ascontiguousarray(img).reshape(-1))
+    d_dst = torch.zeros(max(w * h // 2, 8), dtype=torch.uint8, device="cuda")
+    rc = gb.encode_device(codec, d_dst, d_src, w, h, stride)
+    torch.cuda.synchronize()
+    return rc, d_dst.cpu().numpy()[: w * h // 2]
+
+
+def gpu_host(codec, img, w, h, stride=None):
+    stride = w * 4 if stride is None else stride
+    out = np.zeros(w * h // 2, dtype=np.uint8)
+    rc = HOST_FN[codec](out, aligned_copy(img), w, h, stride)
+    return rc, out
+
+
+def test_library_sees_a_gpu():
+    assert gb.device_count() >= 1
+    assert "B200" in torch.cuda.get_device_name(0) or torch.cuda.get_device_capability(0)[0] >= 10
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_golden_fixtures(codec):
+    """Committed fixtures produced by the unmodified reference (tests/golden/make_golden.py)."""
+    fx = np.load("tests/golden/fixtures.npz")
+    key = {DXT1: "dxt1", ETC1: "etc1"}[codec]
+    names = sorted(k[:-5] for k in fx.files if k.endswith("_rgba"))
+    assert len(names) >= 39
+    for n in names:
+        img = fx[n + "_rgba"]
+        h, w = img.shape[:2]
+        rc, got = gpu_device(codec, img, w, h)
+        assert rc == 0
+        assert np.array_equal(got, fx[f"{n}_{key}"]), n
+        rc, got = gpu_host(codec, img, w, h)
+        assert rc == 0 and np.array_equal(got, fx[f"{n}_{key}"]), n
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_all_test_images_match_golden_hashes_and_oracle(codec, oracle, golden):
+    names = test_image_names()
+    if not names:
+        pytest.skip("oracle/_ref/test-data not present")
+    key = {DXT1: "dxt1", ETC1: "etc1"}[codec]
+    for n in names:
+        img = load_test_image(n)
+        h, w = img.shape[:2]
+        rc, got = gpu_device(codec, img, w, h)
+        assert rc == 0
+        assert hashlib.sha256(got.tobytes()).hexdigest() == golden["images"][n][key]["sha256"], n
+        assert np.array_equal(got, oracle.compress(codec, img, w, h)[1]), n
+
+
+@pytest.mark.parametrize("codec", CODECS)
+@pytest.mark.parametrize("family", [0, 1, 2, 3])
+def test_synthetic_families_vs_oracle(codec, family, oracle, golden):
+    img = synth_family(family, 256, 256)
+    rc, got = gpu_device(codec, img, 256, 256)
+    assert rc == 0
+    key = {DXT1: "dxt1", ETC1: "etc1"}[codec]
+    assert hashlib.sha256(got.tobytes()).hexdigest() == golden["synthetic"][f"family{family}_256"][key]["sha256"]
+    img = synth_family(family, 1024, 512, seed=77)
+    rc, got = gpu_device(codec, img, 1024, 512)
+    assert rc == 0 and np.array_equal(got, oracle.compress(codec, img, 1024, 512)[1])
+
+
+@pytest.mark.parametrize("codec", CODECS)
+@pytest.mark.parametrize("shape", [(16, 4), (16, 8), (32, 4), (48, 12), (112, 20), (144, 4), (528, 36), (1040, 8), (4112, 4)])
+def test_ragged_shapes(codec, shape, oracle):
+    w, h = shape
+    img = splitmix_rgba(w * h, seed=w * 131 + h)
+    rc, got = gpu_device(codec, img, w, h)
+    assert rc == 0 and np.array_equal(got, oracle.compress(codec, img, w, h)[1])
+    rc, got = gpu_host(codec, img, w, h)
+    assert rc == 0 and np.array_equal(got, oracle.compress(codec, img, w, h)[1])
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_padded_stride_and_pad_bytes_ignored(codec, oracle):
+    w, h, pad = 320, 64, 256
+    stride = w * 4 + pad
+    tight = synth_family(1, w, h)
+    padded = np.full((h, stride), 0xAB, dtype=np.uint8)
+    padded[:, : w * 4] = tight.reshape(h, w * 4)
+    want = oracle.compress(codec, tight, w, h)[1]
+    for runner in (gpu_device, gpu_host):
+        rc, got = runner(codec, padded, w, h, stride)
+        assert rc == 0 and np.array_equal(got, want)
+    padded[:, w * 4:] = 0x11
+    rc, got = gpu_device(codec, padded, w, h, stride)
+    assert rc == 0 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_alpha_is_ignored(codec):
+    img = synth_family(0, 128, 64)
+    a = img.copy(); a[..., 3] = 255
+    b = img.copy(); b[..., 3] = 0
+    assert np.array_equal(gpu_device(codec, a, 128, 64)[1], gpu_device(codec, b, 128, 64)[1])
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_return_codes_match_reference(codec):
+    """-1 width%16, -2 height%4 in that order, 0 for empty images (goofy_tc.h:1500-1508); output untouched on error."""
+    buf = torch.full((4096,), 0x5A, dtype=torch.uint8, device="cuda")
+    src = torch.zeros(64 * 64 * 4, dtype=torch.uint8, device="cuda")
+    assert gb.encode_device(codec, buf, src, 24, 32, 96) == -1
+    assert gb.encode_device(codec, buf, src, 32, 6, 128) == -2
+    assert gb.encode_device(codec, buf, src, 24, 6, 96) == -1
+    assert gb.encode_device(codec, buf, src, 0, 0, 0) == 0
+    assert gb.encode_device(codec, buf, src, 0, 8, 0) == 0
+    assert gb.encode_device(codec, buf, src, 32, 32, 64) == -5
+    assert gb.encode_device(codec, buf, src, 32, 32, 136) == -4
+    assert gb.encode_device(codec, buf, 0, 32, 32, 128) == -3
+    assert gb.encode_device(codec, buf, src.data_ptr() + 4, 32, 32, 128) == -4
+    assert gb.encode_device(7, buf, src, 32, 32, 128) == -6
+    torch.cuda.synchronize()
+    assert bool((buf == 0x5A).all())
+    out = np.full(512, 0x5A, dtype=np.uint8)
+    img = np.zeros(32 * 32 * 4, dtype=np.uint8)
+    assert HOST_FN[codec](out, img, 24, 32, 96) == -1
+    assert HOST_FN[codec](out, img, 32, 30, 128) == -2
+    assert HOST_FN[codec](out, img, 0, 0, 0) == 0
+    assert (out == 0x5A).all()
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_uniform_batch_and_dual(codec, oracle):
+    n, w, h = 5, 192, 64
+    imgs = np.stack([synth_family(i % 4, w, h, seed=i) for i in range(n)])
+    d_src = dev(imgs)
+    d_dst = torch.zeros((n, w * h // 2), dtype=torch.uint8, device="cuda")
+    rc = gb.encode_batch_uniform_device(codec, d_dst, d_src, w, h, w * 4, w * h * 4, w * h // 2, n)
+    torch.cuda.synchronize()
+    assert rc == 0
+    for i in range(n):
+        assert np.array_equal(d_dst[i].cpu().numpy(), oracle.compress(codec, imgs[i], w, h)[1])
+    if codec == DXT1:
+        d_a = torch.zeros((n, w * h // 2), dtype=torch.uint8, device="cuda")
+        d_b = torch.zeros((n, w * h // 2), dtype=torch.uint8, device="cuda")
+        rc = gb.encode_dual_device(d_a, d_b, d_src, w, h, w * 4, w * h * 4, w * h // 2, n)
+        torch.cuda.synchronize()
+        assert rc == 0
+        for i in range(n):
+            assert np.array_equal(d_a[i].cpu().numpy(), oracle.compress(DXT1, imgs[i], w, h)[1])
+            assert np.array_equal(d_b[i].cpu().numpy(), oracle.compress(ETC1, imgs[i], w, h)[1])
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_ragged_batch_descriptors(codec, oracle):
+    shapes = [(16, 4), (64, 64), (272, 12), (1024, 8), (48, 100), (0, 0), (320, 36)]
+    imgs, srcs, dsts, descs = [], [], [], []
+    for i, (w, h) in enumerate(shapes):
+        img = splitmix_rgba(max(w * h, 1), seed=100 + i)[: w * h * 4]
+        imgs.append(img)
+        srcs.append(dev(img) if w else torch.zeros(16, dtype=torch.uint8, device="cuda"))
+        dsts.append(torch.zeros(max(w * h // 2, 8), dtype=torch.uint8, device="cuda"))
+        descs.append((srcs[-1], dsts[-1], w, h, w * 4))
+    rc = gb.encode_batch_device(codec, descs)
+    torch.cuda.synchronize()
+    assert rc == 0
+    for (w, h), img, d in zip(shapes, imgs, dsts):
+        if w:
+            assert np.array_equal(d.cpu().numpy()[: w * h // 2], oracle.compress(codec, img, w, h)[1]), (w, h)
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_sharded_host_equals_single(codec, oracle):
+    w, h = 512, 200
+    img = synth_family(1, w, h)
+    want = oracle.compress(codec, img, w, h)[1]
+    for n in range(1, gb.device_count() + 1):
+        out = np.zeros(w * h // 2, dtype=np.uint8)
+        assert gb.encode_sharded_host(codec, out, aligned_copy(img), w, h, w * 4, n) == 0
+        assert np.array_equal(out, want), n
+    descs, dsts = [], []
+    for i in range(6):
+        d = i % gb.device_count()
+        with torch.cuda.device(d):
+            s = torch.from_numpy(img.reshape(-1)).cuda(d)
+            t = torch.zeros(w * h // 2, dtype=torch.uint8, device=f"cuda:{d}")
+        dsts.append(t)
+        descs.append((s, t, w, h, w * 4, d))
+    assert gb.encode_batch_sharded(codec, descs) == 0
+    for t in dsts:
+        assert np.array_equal(t.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_full_size_8192_properties(codec, oracle, reference):
+    """BASELINE.json configs[1]/[2] at full size: bit-exact vs the unmodified reference run row-parallel on the
+    host, strip-concatenation equivalence, determinism, and a decode/PSNR sanity check."""
+    size = 8192
+    src = torch.empty((size, size, 4), dtype=torch.uint8, device="cuda")
+    from bench import fill_texture_device
+    fill_texture_device(torch, src, seed=5)
+    dst = torch.zeros(size * size // 2, dtype=torch.uint8, device="cuda")
+    assert gb.encode_device(codec, dst, src, size, size, size * 4) == 0
+    torch.cuda.synchronize()
+    got = dst.cpu().numpy()
+    host = aligned_copy(src.cpu().numpy())
+    rc, want = reference.compress_mt(codec, host, size, size, size * 4, reference.hardware_threads())
+    assert rc == 0 and np.array_equal(got, want)
+    # strips of whole block rows, encoded separately, concatenate to the same bytes (the multi-GPU partition)
+    dst2 = torch.zeros_like(dst)
+    for g in range(8):
+        first, count = gb.strip_partition(size, 8, g)
+        off_src = first * 4 * size * 4
+        off_dst = first * (size // 4) * 8
+        assert gb.encode_device(codec, dst2[off_dst:], src.view(-1)[off_src:], size, count * 4, size * 4) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(dst, dst2)
+    # decode a 512-row band and check quality is in the encoder's known range
+    band = 512
+    dec = oracle.decode(codec, got[: size * band // 2], size, band)
+    p = __import__("oracle.oracle", fromlist=["psnr_from_sse"]).psnr_from_sse(oracle.sse_rgb(dec, host[: size * band * 4]), size * band)
+    assert 30.0 < p["psnr_rgb768"] < 60.0
