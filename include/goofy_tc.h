@@ -1,0 +1,98 @@
+// goofy_tc.h -- drop-in replacement for the reference's GoofyTC/goofy_tc.h, backed by B200 kernels.
+//
+// The two public functions keep the reference's names, namespace, argument order and return
+// codes byte for byte (GoofyTC/goofy_tc.h:10-13), so existing callers -- including code that
+// takes their address as `int (*)(unsigned char*, const unsigned char*, unsigned, unsigned,
+// unsigned)` like the reference harness does (Src/main.cpp:644) -- only need to re-link
+// against libgoofy_b200.so:
+//
+//     #define GOOFYTC_IMPLEMENTATION      // the reference's usage idiom (README.md:93-95)
+//     #include <goofy_tc.h>               // ... still works; the macro is simply not needed
+//     goofy::compressDXT1(result, input, width, height, stride);
+//
+// Unlike the reference (which force-defines GOOFYTC_IMPLEMENTATION at :34 and so can be included
+// from one translation unit only) the wrappers here are inline and safe to include everywhere.
+// All work is done by hand-written sm_100a CUDA kernels; there is no CPU fallback -- without a
+// B200 the calls return GOOFY_B200_E_DEVICE.
+//
+// namespace goofy::b200 adds the batched, device-resident and multi-GPU variants.
+#ifndef GOOFY_TC_B200_H
+#define GOOFY_TC_B200_H
+
+#include <cstddef>
+#include <cstdint>
+
+#include "goofy_b200.h"
+
+namespace goofy {
+
+int compressDXT1(unsigned char* result, const unsigned char* input, unsigned int width, unsigned int height, unsigned int stride);
+int compressETC1(unsigned char* result, const unsigned char* input, unsigned int width, unsigned int height, unsigned int stride);
+
+// Host buffers in, host buffers out.  0 ok, -1 width % 16, -2 height % 4 (reference codes);
+// other negative values are GOOFY_B200_E_* (goofy_b200.h).
+inline int compressDXT1(unsigned char* result, const unsigned char* input, unsigned int width, unsigned int height, unsigned int stride)
+{
+    return goofy_b200_compress_dxt1(result, input, width, height, stride);
+}
+
+inline int compressETC1(unsigned char* result, const unsigned char* input, unsigned int width, unsigned int height, unsigned int stride)
+{
+    return goofy_b200_compress_etc1(result, input, width, height, stride);
+}
+
+namespace b200 {
+
+enum Codec : int { DXT1 = GOOFY_B200_DXT1, ETC1 = GOOFY_B200_ETC1 };
+using Image = ::GoofyB200Image;
+
+inline int deviceCount() { return goofy_b200_device_count(); }
+inline const char* errorString(int code) { return goofy_b200_error_string(code); }
+
+// Device pointers on the current device, asynchronous on `stream` (a cudaStream_t).
+inline int encode(Codec codec, void* dResult, const void* dInput, uint32_t width, uint32_t height, uint32_t stride,
+                  void* stream = nullptr)
+{
+    return goofy_b200_encode_device(codec, dResult, dInput, width, height, stride, stream);
+}
+
+// n images of one shape at fixed pitches.
+inline int encodeBatch(Codec codec, void* dResult, const void* dInput, uint32_t width, uint32_t height, uint32_t stride,
+                       uint64_t inputImagePitch, uint64_t resultImagePitch, uint32_t nImages, void* stream = nullptr)
+{
+    return goofy_b200_encode_batch_uniform_device(codec, dResult, dInput, width, height, stride, inputImagePitch,
+                                                  resultImagePitch, nImages, stream);
+}
+
+// DXT1 and ETC1s from a single read of the input.
+inline int encodeDual(void* dResultDxt1, void* dResultEtc1, const void* dInput, uint32_t width, uint32_t height,
+                      uint32_t stride, uint64_t inputImagePitch = 0, uint64_t resultImagePitch = 0, uint32_t nImages = 1,
+                      void* stream = nullptr)
+{
+    return goofy_b200_encode_dual_device(dResultDxt1, dResultEtc1, dInput, width, height, stride, inputImagePitch,
+                                         resultImagePitch, nImages, stream);
+}
+
+// Images of arbitrary shapes on the current device, one launch.
+inline int encodeBatch(Codec codec, const Image* images, uint32_t nImages, void* stream = nullptr)
+{
+    return goofy_b200_encode_batch_device(codec, images, nImages, stream);
+}
+
+// Images spread over several GPUs (Image::device), one host thread per device, no collectives.
+inline int encodeBatchSharded(Codec codec, const Image* images, uint32_t nImages)
+{
+    return goofy_b200_encode_batch_sharded(codec, images, nImages);
+}
+
+// One host image cut into horizontal strips, strip g on GPU g.
+inline int encodeSharded(Codec codec, unsigned char* result, const unsigned char* input, uint32_t width, uint32_t height,
+                         uint32_t stride, int nGpus = 0)
+{
+    return goofy_b200_encode_sharded_host(codec, result, input, width, height, stride, nGpus);
+}
+
+}  // namespace b200
+}  // namespace goofy
+
+#endif  // GOOFY_TC_B200_H

@@ -220,7 +220,7 @@ def load_test_image(name: str) -> np.ndarray:
     return a
 
 
-def test_image_names() -> list[str]:
+def image_names() -> list[str]:
     """Images the reference harness can load: width%16==0 and height%4==0 (Src/main.cpp:298-307)."""
     if not TEST_DATA_DIR.is_dir():
         return []

@@ -21,7 +21,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from oracle.oracle import (DXT1, ETC1, Reference, aligned_copy, load_test_image, synth_family,  # noqa: E402
-                           test_image_names, xorshift_bytes)
+                           image_names, xorshift_bytes)
 
 HERE = Path(__file__).resolve().parent
 
@@ -37,7 +37,7 @@ def main():
            "images": {}, "synthetic": {}, "known_answer": {}}
     fixtures = {}
 
-    for name in test_image_names():
+    for name in image_names():
         img = load_test_image(name)
         h, w = img.shape[:2]
         flat = aligned_copy(img)

@@ -1,0 +1,48 @@
+"""The CUDA block codec's arithmetic (goofy_b200/csrc/block_codec.cuh) compiled for the host with the
+device intrinsics emulated, against the oracle.  This checks the kernel SOURCE on a machine without a
+GPU; the GPU tests (-m gpu) check the compiled kernel itself."""
+import numpy as np
+import pytest
+
+from oracle.oracle import DXT1, ETC1, splitmix_rgba, synth_family
+
+CODECS = [DXT1, ETC1]
+KEY = {DXT1: "dxt1", ETC1: "etc1"}
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_kernel_math_on_fixtures(codec, kernel_math):
+    fx = np.load("tests/golden/fixtures.npz")
+    for n in sorted(k[:-5] for k in fx.files if k.endswith("_rgba")):
+        img = fx[n + "_rgba"]
+        h, w = img.shape[:2]
+        rc, got = kernel_math(codec, img, w, h)
+        assert rc == 0 and np.array_equal(got, fx[f"{n}_{KEY[codec]}"]), n
+
+
+@pytest.mark.parametrize("codec", CODECS)
+@pytest.mark.parametrize("family", [0, 1, 2, 3])
+def test_kernel_math_on_synthetic(codec, family, kernel_math, oracle):
+    img = synth_family(family, 512, 512, seed=1234 + family)
+    rc, got = kernel_math(codec, img, 512, 512)
+    assert rc == 0 and np.array_equal(got, oracle.compress(codec, img, 512, 512)[1])
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_kernel_math_low_contrast_sweep(codec, kernel_math, oracle):
+    rng = np.random.default_rng(7)
+    for spread in (0, 1, 2, 5, 8, 9, 21, 22, 44, 74, 106, 152, 182, 254, 255):
+        base = rng.integers(0, 256 - spread, size=(64, 64, 1, 1, 3))
+        blk = base + rng.integers(0, spread + 1, size=(64, 64, 4, 4, 3))
+        img = np.zeros((256, 256, 4), dtype=np.uint8)
+        img[..., :3] = blk.transpose(0, 2, 1, 3, 4).reshape(256, 256, 3)
+        img[..., 3] = rng.integers(0, 256, size=(256, 256))
+        rc, got = kernel_math(codec, img, 256, 256)
+        assert rc == 0 and np.array_equal(got, oracle.compress(codec, img, 256, 256)[1]), spread
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_kernel_math_return_codes(codec, kernel_math):
+    img = splitmix_rgba(64 * 64, seed=1)
+    assert kernel_math(codec, img, 24, 32)[0] == -1
+    assert kernel_math(codec, img, 32, 6)[0] == -2
