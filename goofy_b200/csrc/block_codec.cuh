@@ -123,7 +123,9 @@ GB_DEV void encode_dxt1(const uint32_t (&p)[16], const BlockFront& f, uint32_t& 
 
 // ---------------------------------------------------------------------------------------- ETC1s
 // floor((a+b)/2) on four bytes at once
-GB_DEV uint32_t floor_avg4(uint32_t a, uint32_t b) { return (a & b) + (((a ^ b) & 0xFEFEFEFEu) >> 1); }
+GB_DEV uint32_t floor_avg4(uint32_t a, uint32_t b) { return (a & b) + (xor_and(a, b, 0xFEFEFEFEu) >> 1); }
+// floor_avg4(~a, ~b) without materialising the complements
+GB_DEV uint32_t floor_avg4_of_complements(uint32_t a, uint32_t b) { return ~(a | b) + (xor_and(a, b, 0xFEFEFEFEu) >> 1); }
 
 // Output (goofy_tc.h:1358-1493): word0 = R5<<3 | G5<<11 | B5<<19 | control<<24;
 // word1 = ~(GezPlane | LqtPlane << 16), pixel (x,y) at plane bit ((x^2)<<2)+y.
@@ -150,8 +152,8 @@ GB_DEV void encode_etc1(const uint32_t (&p)[16], const BlockFront& f, const uint
     uint32_t col[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
-        const uint32_t top = floor_avg4(~p[x], ~p[4 + x]);
-        const uint32_t bot = floor_avg4(~p[8 + x], ~p[12 + x]);
+        const uint32_t top = floor_avg4_of_complements(p[x], p[4 + x]);
+        const uint32_t bot = floor_avg4_of_complements(p[8 + x], p[12 + x]);
         col[x] = floor_avg4(top, bot);
     }
     const uint32_t avg = ~floor_avg4(floor_avg4(col[0], col[1]), floor_avg4(col[2], col[3]));

@@ -91,7 +91,11 @@ int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream)
             Q.dst += (uint64_t)img0 * P.dstPitch;
             if (Q.dst2) Q.dst2 += (uint64_t)img0 * P.dstPitch;
             const dim3 grid(gx, (rows + ty - 1u) / ty, nz);
-            gb::encode_direct_kernel<MODE><<<grid, block, 0, stream>>>(Q);
+            // 32-bit in-image offsets unless the image spans 4 GiB or more
+            if ((uint64_t)P.bh * 4u * P.stride + (uint64_t)P.bw * 16u < 0xFFFFFFFFull)
+                gb::encode_direct_kernel<MODE, false><<<grid, block, 0, stream>>>(Q);
+            else
+                gb::encode_direct_kernel<MODE, true><<<grid, block, 0, stream>>>(Q);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             GB_CUDA(cudaGetLastError());
         }

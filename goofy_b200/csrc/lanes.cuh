@@ -38,6 +38,14 @@ GB_DEV uint32_t min2_u16x2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
 GB_DEV uint32_t max2_u16x2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
 // per-lane clamp(a + b, 0, c) on two signed 16-bit lanes
 GB_DEV uint32_t addclamp_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2_relu(a, b, c); }
+// (a ^ b) & m as ONE LOP3.  Written in PTX so the compiler cannot re-associate the mask past a
+// following shift (it would, and that costs an extra instruction per average).
+GB_DEV uint32_t xor_and(uint32_t a, uint32_t b, uint32_t m)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(r) : "r"(a), "r"(b), "r"(m));
+    return r;
+}
 
 #else  // host emulation (tests only)
 
@@ -78,6 +86,8 @@ GB_DEV uint32_t addclamp_s16x2(uint32_t a, uint32_t b, uint32_t c)
     }
     return r;
 }
+
+GB_DEV uint32_t xor_and(uint32_t a, uint32_t b, uint32_t m) { return (a ^ b) & m; }
 
 #endif
 

@@ -1,0 +1,80 @@
+// membench.cu -- what HBM bandwidth can a streaming kernel with the encoders' access pattern reach?
+// Diagnostic tool (not part of libgoofy_b200.so).  Read-mostly probes with the same 8:1 read:write
+// ratio as the encoders, so the roofline fraction in bench.py can be read against a like-for-like
+// ceiling rather than against a 1:1 copy.
+//   linear   : each thread reads 64 contiguous bytes (4 x LDG.128), writes 8
+//   rows4    : each thread reads 16 bytes from 4 rows `stride` apart (the encoders' pattern), writes 8
+//   copy     : 16 B in, 16 B out (STREAM copy, what MEASURED_PEAKS.json's hbm_gbs is)
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+
+__device__ __forceinline__ uint4 ldg_na(const void* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_rows4(const uint8_t* src, uint8_t* dst, uint32_t bw, uint32_t stride)
+{
+    const uint32_t bx = blockIdx.x * 256 + threadIdx.x, by = blockIdx.y;
+    const uint8_t* s = src + (size_t)by * 4 * stride + (size_t)bx * 16;
+    uint4 a = ldg_na(s), b = ldg_na(s + stride), c = ldg_na(s + 2 * (size_t)stride), d = ldg_na(s + 3 * (size_t)stride);
+    uint2 o;
+    o.x = a.x ^ b.y ^ c.z ^ d.w ^ a.z ^ b.w ^ c.x ^ d.y;
+    o.y = a.y ^ b.z ^ c.w ^ d.x ^ a.w ^ b.x ^ c.y ^ d.z;
+    *(uint2*)(dst + ((size_t)by * bw + bx) * 8) = o;
+}
+
+__global__ void __launch_bounds__(256) k_linear(const uint8_t* src, uint8_t* dst)
+{
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t warp = t >> 5, lane = t & 31;
+    const uint8_t* s = src + warp * 2048 + lane * 16;  // a warp reads 2 KiB contiguous as 4 x 512 B
+    uint4 a = ldg_na(s), b = ldg_na(s + 512), c = ldg_na(s + 1024), d = ldg_na(s + 1536);
+    uint2 o;
+    o.x = a.x ^ b.y ^ c.z ^ d.w ^ a.z ^ b.w ^ c.x ^ d.y;
+    o.y = a.y ^ b.z ^ c.w ^ d.x ^ a.w ^ b.x ^ c.y ^ d.z;
+    *(uint2*)(dst + t * 8) = o;
+}
+
+__global__ void __launch_bounds__(256) k_copy(const uint4* src, uint4* dst, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) dst[i] = src[i];
+}
+
+int main()
+{
+    const uint32_t W = 8192, H = 8192, bw = W / 4, bh = H / 4, stride = W * 4;
+    const size_t inBytes = (size_t)W * H * 4, outBytes = inBytes / 8;
+    const int NBUF = 4;
+    uint8_t* src[NBUF]; uint8_t* dst[NBUF];
+    for (int i = 0; i < NBUF; ++i) { cudaMalloc(&src[i], inBytes); cudaMalloc(&dst[i], inBytes); cudaMemset(src[i], i + 1, inBytes); }
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto timeit = [&](const char* name, double bytes, auto launch) {
+        for (int i = 0; i < 8; ++i) launch(i % NBUF);
+        cudaDeviceSynchronize();
+        const int iters = 100;
+        cudaEventRecord(e0);
+        for (int i = 0; i < iters; ++i) launch(i % NBUF);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("%-8s %8.2f us/launch  %8.1f GB/s\n", name, ms / iters * 1e3, bytes / (ms / iters * 1e-3) / 1e9);
+    };
+    timeit("rows4", (double)inBytes + outBytes, [&](int b) { k_rows4<<<dim3(bw / 256, bh), 256>>>(src[b], dst[b], bw, stride); });
+    timeit("linear", (double)inBytes + outBytes, [&](int b) { k_linear<<<(unsigned)(inBytes / 64 / 256), 256>>>(src[b], dst[b]); });
+    timeit("copy", 2.0 * inBytes, [&](int b) { k_copy<<<148 * 16, 256>>>((const uint4*)src[b], (uint4*)dst[b], inBytes / 16); });
+    {
+        float best = 1e9f;
+        for (int i = 0; i < 10; ++i) {
+            cudaEventRecord(e0); cudaMemcpyAsync(dst[i % NBUF], src[i % NBUF], inBytes, cudaMemcpyDeviceToDevice); cudaEventRecord(e1);
+            cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+        }
+        printf("%-8s %8.2f us/launch  %8.1f GB/s (cudaMemcpy D2D, best of 10)\n", "memcpy", best * 1e3, 2.0 * inBytes / (best * 1e-3) / 1e9);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
