@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--codec", choices=["dxt1", "etc1"], default="dxt1")
     ap.add_argument("--size", type=int, default=8192, help="texture width = height")
     ap.add_argument("--batch", type=int, default=4, help="distinct textures per step")
+    ap.add_argument("--load-path", choices=["auto", "direct", "tma"], default="auto",
+                    help="image load layer of the device entry points (see include/goofy_b200.h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -223,6 +225,7 @@ def run_b200_arm(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    gb.set_load_path({"auto": gb.LOAD_AUTO, "direct": gb.LOAD_DIRECT, "tma": gb.LOAD_TMA}[args.load_path])
     codec = gb.DXT1 if args.codec == "dxt1" else gb.ETC1
     size, batch = args.size, args.batch
     stride = size * 4
@@ -347,6 +350,7 @@ def run_b200_arm(args):
                        "pixels_per_step_per_gpu": px_per_step, "stride": stride,
                        "l2": f"inputs larger than L2: {batch} distinct {size * size * 4 >> 20} MiB textures rotate, "
                              f"each launch streams {int(size * size * BYTES_PER_PIXEL) >> 20} MiB",
+                       "load_path": args.load_path,
                        "sharding": "one batch per rank, no collectives" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,

@@ -10,11 +10,13 @@ The implementation is libgoofy_b200.so (CUDA only; there is no CPU fallback).
 from .api import (DXT1, ETC1, CODEC_NAMES, GoofyError, check, compressDXT1, compressETC1, device_count,
                   encode_batch_device, encode_batch_sharded, encode_batch_uniform_device, encode_device,
                   encode_dual_device, encode_host, encode_sharded_host, error_string, kernel_launches,
-                  make_descriptors, output_bytes, strip_partition)
+                  make_descriptors, output_bytes, strip_partition, set_load_path, get_load_path, LOAD_AUTO,
+                  LOAD_DIRECT, LOAD_TMA)
 
 __all__ = [
     "DXT1", "ETC1", "CODEC_NAMES", "GoofyError", "check", "compressDXT1", "compressETC1", "device_count",
     "encode_batch_device", "encode_batch_sharded", "encode_batch_uniform_device", "encode_device",
     "encode_dual_device", "encode_host", "encode_sharded_host", "error_string", "kernel_launches",
-    "make_descriptors", "output_bytes", "strip_partition",
+    "make_descriptors", "output_bytes", "strip_partition", "set_load_path", "get_load_path", "LOAD_AUTO",
+    "LOAD_DIRECT", "LOAD_TMA",
 ]

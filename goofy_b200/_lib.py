@@ -32,6 +32,8 @@ PROTOTYPES = {
     "goofy_b200_device_count": (_int, []),
     "goofy_b200_error_string": (C.c_char_p, [_int]),
     "goofy_b200_kernel_launches": (_u64, []),
+    "goofy_b200_set_load_path": (_int, [_int]),
+    "goofy_b200_get_load_path": (_int, []),
     "goofy_b200_compress_dxt1": (_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_uint]),
     "goofy_b200_compress_etc1": (_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_uint]),
     "goofy_b200_encode_host": (_int, [_int, _vp, _vp, _u32, _u32, _u32]),

@@ -43,6 +43,18 @@ def kernel_launches() -> int:
     return int(_lib.load().goofy_b200_kernel_launches())
 
 
+LOAD_AUTO, LOAD_DIRECT, LOAD_TMA = 0, 1, 2
+
+
+def set_load_path(path: int) -> int:
+    """Pick the image load layer for the uniform device entry points; returns the previous setting."""
+    return int(_lib.load().goofy_b200_set_load_path(path))
+
+
+def get_load_path() -> int:
+    return int(_lib.load().goofy_b200_get_load_path())
+
+
 def output_bytes(width: int, height: int) -> int:
     return width * height // 2
 

@@ -125,7 +125,7 @@ GB_DEV void encode_dxt1(const uint32_t (&p)[16], const BlockFront& f, uint32_t& 
 // floor((a+b)/2) on four bytes at once
 GB_DEV uint32_t floor_avg4(uint32_t a, uint32_t b) { return (a & b) + (xor_and(a, b, 0xFEFEFEFEu) >> 1); }
 // floor_avg4(~a, ~b) without materialising the complements
-GB_DEV uint32_t floor_avg4_of_complements(uint32_t a, uint32_t b) { return ~(a | b) + (xor_and(a, b, 0xFEFEFEFEu) >> 1); }
+GB_DEV uint32_t floor_avg4_of_complements(uint32_t a, uint32_t b) { return nor(a, b) + (xor_and(a, b, 0xFEFEFEFEu) >> 1); }
 
 // Output (goofy_tc.h:1358-1493): word0 = R5<<3 | G5<<11 | B5<<19 | control<<24;
 // word1 = ~(GezPlane | LqtPlane << 16), pixel (x,y) at plane bit ((x^2)<<2)+y.
@@ -159,21 +159,17 @@ GB_DEV void encode_etc1(const uint32_t (&p)[16], const BlockFront& f, const uint
     const uint32_t avg = ~floor_avg4(floor_avg4(col[0], col[1]), floor_avg4(col[2], col[3]));
 
     // Shift the average colour so its brightness becomes `mid` (goofy_tc.h:1431-1449):
-    // base = clamp(avg + d, 0, 255) per channel with d = clamp(mid - Y(avg), -127, 127).
+    // base = clamp(avg + d, 0, 255) per channel with d = clamp(mid - Y(avg), -127, 127), then
+    // to5(base) = (max(base,1) - 1) >> 3.  Both clamps fold into one: max(base,1) - 1 ==
+    // clamp(avg + (d - 1), 0, 254), and "& 0xF8" leaves to5 << 3 in place.
     const int avgY = (int)(dp4a(avg, kLuma, 3u) >> 2);
-    int d = (int)f.mid - avgY;
-    d = d < -127 ? -127 : d;
-    d = d > 127 ? 127 : d;
-    const uint32_t d2 = prmt((uint32_t)d, 0u, 0x1010);
-    const uint32_t rb = addclamp_s16x2(avg & 0x00FF00FFu, d2, 0x00FF00FFu);  // lanes (R, B)
-    int g = (int)((avg >> 8) & 0xFFu) + d;
-    g = g < 0 ? 0 : g;
-    g = g > 255 ? 255 : g;
-
-    // to5, already positioned: (max(v,1)-1) & 0xF8 is to5(v) << 3
-    const uint32_t rb5 = (max2_u16x2(rb, 0x00010001u) - 0x00010001u) & 0x00F800F8u;
-    const uint32_t g5 = (uint32_t)((g > 1 ? g : 1) - 1) & 0xF8u;
-    word0 = rb5 | (g5 << 8) | controlLut[f.range];
+    int dm1 = (int)f.mid - 1 - avgY;              // d - 1
+    dm1 = dm1 < -128 ? -128 : dm1;
+    dm1 = dm1 > 126 ? 126 : dm1;
+    const uint32_t d2 = prmt((uint32_t)dm1, 0u, 0x1010);
+    const uint32_t rb = addclamp_s16x2(avg & 0x00FF00FFu, d2, 0x00FE00FEu);   // lanes (R, B)
+    const uint32_t g = (uint32_t)addclamp_s32((int)((avg >> 8) & 0xFFu), dm1, 254);
+    word0 = (rb & 0x00F800F8u) | ((g & 0xF8u) << 8) | controlLut[f.range];
 }
 
 // The reference's table (goofy_tc.h:1040-1057) steps at 22,44,74,106,152,182,254 and holds

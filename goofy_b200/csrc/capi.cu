@@ -9,6 +9,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -18,6 +19,7 @@
 
 #include "../../include/goofy_b200.h"
 #include "encode_kernels.cuh"
+#include "tma_kernels.cuh"
 
 namespace {
 
@@ -70,9 +72,27 @@ int check_pointers(const void* src, const void* dst)
     return GOOFY_B200_OK;
 }
 
+template <int MODE, bool PITCHED>
+int launch_direct_grid(const gb::EncodeParams& Q, dim3 grid, dim3 block, cudaStream_t stream)
+{
+    // 32-bit in-image offsets unless the image spans 4 GiB or more
+    if ((uint64_t)Q.bh * 4u * Q.stride + (uint64_t)Q.bw * 16u < 0xFFFFFFFFull)
+        gb::encode_direct_kernel<MODE, false, PITCHED><<<grid, block, 0, stream>>>(Q);
+    else
+        gb::encode_direct_kernel<MODE, true, PITCHED><<<grid, block, 0, stream>>>(Q);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
 template <int MODE>
 int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream)
 {
+    // A batch whose images lie back to back (pitch == image size) is one tall image.
+    const uint64_t imageBytes = (uint64_t)P.bh * 4u * P.stride, outBytes = (uint64_t)P.bh * P.bw * 8u;
+    if (nImages > 1u && P.srcPitch == imageBytes && P.dstPitch == outBytes && (uint64_t)P.bh * nImages <= 0xFFFFFFFFull) {
+        P.bh *= nImages;
+        nImages = 1u;
+    }
     // threads: x walks blocks along a row (coalescing), y stacks block rows for narrow images
     // (x is a power of two and x*y == 256: the kernels rely on exactly 256 threads)
     uint32_t tx = 32u;
@@ -91,16 +111,130 @@ int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream)
             Q.dst += (uint64_t)img0 * P.dstPitch;
             if (Q.dst2) Q.dst2 += (uint64_t)img0 * P.dstPitch;
             const dim3 grid(gx, (rows + ty - 1u) / ty, nz);
-            // 32-bit in-image offsets unless the image spans 4 GiB or more
-            if ((uint64_t)P.bh * 4u * P.stride + (uint64_t)P.bw * 16u < 0xFFFFFFFFull)
-                gb::encode_direct_kernel<MODE, false><<<grid, block, 0, stream>>>(Q);
-            else
-                gb::encode_direct_kernel<MODE, true><<<grid, block, 0, stream>>>(Q);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            GB_CUDA(cudaGetLastError());
+            const int rc = nImages > 1u ? launch_direct_grid<MODE, true>(Q, grid, block, stream)
+                                        : launch_direct_grid<MODE, false>(Q, grid, block, stream);
+            if (rc != GOOFY_B200_OK) return rc;
         }
     }
     return GOOFY_B200_OK;
+}
+
+// ---------------------------------------------------------------- TMA tile path
+std::atomic<int> g_loadPath{GOOFY_B200_LOAD_AUTO};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+struct DeviceInfo {
+    int smCount = 0;
+    int tmaCtasPerSm[3] = {0, 0, 0};  // 0 = not yet configured
+};
+
+// Depth of the tile ring.  GOOFY_B200_TMA_STAGES overrides it for experiments (2..8).
+uint32_t tma_stages()
+{
+    static const uint32_t n = []() -> uint32_t {
+        const char* e = getenv("GOOFY_B200_TMA_STAGES");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 2 && v <= gb::kTmaMaxStages) ? (uint32_t)v : 2u;
+    }();
+    return n;
+}
+DeviceInfo g_devInfo[kMaxDevices];
+std::mutex g_devInfoMutex;
+
+gb::FastDiv make_fastdiv(uint32_t d)
+{
+    gb::FastDiv f;
+    f.d = d;
+    f.m = ((1ull << 40) + d - 1u) / d;
+    return f;
+}
+
+// Shapes the tile kernel's index arithmetic covers (FastDiv ranges, tensor-map limits).
+bool tma_eligible(uint32_t bw, uint32_t bh, uint32_t stride, uint64_t srcPitch, uint32_t nImages)
+{
+    const uint64_t tilesX = (bw + gb::kTmaThreads - 1u) / gb::kTmaThreads;
+    const uint64_t nTiles = tilesX * bh * nImages;
+    if (bh > 65536u || tilesX > 65536u || nTiles >= (1ull << 24)) return false;
+    if (nImages > 1u && (srcPitch % 16u != 0u || srcPitch >= (1ull << 40))) return false;
+    if ((uint64_t)stride * bh * 4u >= (1ull << 40)) return false;
+    return tensor_map_encoder() != nullptr;
+}
+
+template <int MODE>
+int launch_tma(void* dst, void* dst2, const void* src, uint32_t width, uint32_t height, uint32_t stride, uint64_t srcPitch,
+               uint64_t dstPitch, uint32_t nImages, cudaStream_t stream, int dev)
+{
+    CUtensorMap map;
+    const cuuint64_t dims[3] = {width, height, nImages};
+    const cuuint64_t strides[2] = {stride, nImages > 1u ? srcPitch : (cuuint64_t)stride * height};
+    const cuuint32_t box[3] = {(cuuint32_t)gb::kTmaBoxPixels, 4u, 1u};
+    const cuuint32_t elemStrides[3] = {1u, 1u, 1u};
+    const CUresult r = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(src), dims, strides, box,
+                                            elemStrides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return GOOFY_B200_E_ARGS;
+
+    const uint32_t nStages = tma_stages();
+    const int smemBytes = (int)nStages * gb::kTmaStageBytes;
+    int smCount = 0, ctasPerSm = 0;
+    {
+        std::lock_guard<std::mutex> g(g_devInfoMutex);
+        DeviceInfo& di = g_devInfo[dev];
+        if (di.smCount == 0) GB_CUDA(cudaDeviceGetAttribute(&di.smCount, cudaDevAttrMultiProcessorCount, dev));
+        if (di.tmaCtasPerSm[MODE] == 0) {
+            GB_CUDA(cudaFuncSetAttribute(gb::encode_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+            int n = 0;
+            GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gb::encode_tma_kernel<MODE>, gb::kTmaThreads, smemBytes));
+            di.tmaCtasPerSm[MODE] = n > 0 ? n : 1;
+        }
+        smCount = di.smCount;
+        ctasPerSm = di.tmaCtasPerSm[MODE];
+    }
+    gb::TmaParams P;
+    P.dst = (uint8_t*)dst;
+    P.dst2 = (uint8_t*)dst2;
+    P.dstPitch = dstPitch;
+    P.bw = width / 4u;
+    P.bh = height / 4u;
+    const uint32_t tilesX = (P.bw + gb::kTmaThreads - 1u) / gb::kTmaThreads;
+    P.nTiles = tilesX * P.bh * nImages;
+    P.nStages = nStages;
+    P.tilesX = make_fastdiv(tilesX);
+    P.rows = make_fastdiv(P.bh);
+    // persistent CTAs: as many as are resident at once, never more than there are tiles
+    uint32_t grid = (uint32_t)smCount * (uint32_t)ctasPerSm;
+    if (grid > P.nTiles) grid = P.nTiles;
+    gb::encode_tma_kernel<MODE><<<grid, gb::kTmaThreads, smemBytes, stream>>>(map, P);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
+// Which load layer serves a uniform launch.  AUTO: see DESIGN.md section 3 ("load path policy").
+bool choose_tma(uint32_t bw, uint32_t bh, uint32_t stride, uint64_t srcPitch, uint32_t nImages)
+{
+    const int path = g_loadPath.load(std::memory_order_relaxed);
+    if (path == GOOFY_B200_LOAD_DIRECT) return false;
+    if (!tma_eligible(bw, bh, stride, srcPitch, nImages)) return false;
+    if (path == GOOFY_B200_LOAD_TMA) return true;
+    return false;
 }
 
 int encode_uniform(int mode, void* dst, void* dst2, const void* src, uint32_t width, uint32_t height, uint32_t stride,
@@ -116,8 +250,18 @@ int encode_uniform(int mode, void* dst, void* dst2, const void* src, uint32_t wi
         if (rc != GOOFY_B200_OK) return rc;
     }
     if (nImages > 1u && ((srcPitch & 15u) != 0u || (dstPitch & 7u) != 0u)) return GOOFY_B200_E_ALIGN;
-    rc = ensure_device_ready();
+    int dev = -1;
+    rc = ensure_device_ready(&dev);
     if (rc != GOOFY_B200_OK) return rc;
+
+    if (choose_tma(width / 4u, height / 4u, stride, srcPitch, nImages)) {
+        switch (mode) {
+            case gb::kDxt1: return launch_tma<gb::kDxt1>(dst, dst2, src, width, height, stride, srcPitch, dstPitch, nImages, stream, dev);
+            case gb::kEtc1: return launch_tma<gb::kEtc1>(dst, dst2, src, width, height, stride, srcPitch, dstPitch, nImages, stream, dev);
+            case gb::kDual: return launch_tma<gb::kDual>(dst, dst2, src, width, height, stride, srcPitch, dstPitch, nImages, stream, dev);
+            default: return GOOFY_B200_E_CODEC;
+        }
+    }
 
     gb::EncodeParams P;
     P.src = (const uint8_t*)src;
@@ -409,6 +553,14 @@ int goofy_b200_abi_version(void) { return GOOFY_B200_ABI_VERSION; }
 int goofy_b200_device_count(void) { return device_count(); }
 
 uint64_t goofy_b200_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int goofy_b200_set_load_path(int path)
+{
+    if (path < GOOFY_B200_LOAD_AUTO || path > GOOFY_B200_LOAD_TMA) return GOOFY_B200_E_ARGS;
+    return g_loadPath.exchange(path, std::memory_order_relaxed);
+}
+
+int goofy_b200_get_load_path(void) { return g_loadPath.load(std::memory_order_relaxed); }
 
 const char* goofy_b200_error_string(int code)
 {

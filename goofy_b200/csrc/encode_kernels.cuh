@@ -58,7 +58,9 @@ __device__ __forceinline__ void store_block(uint8_t* p, uint32_t w0, uint32_t w1
 // WIDE = false: every byte offset inside one image fits 32 bits (the launcher checks), which
 // keeps the address arithmetic to a handful of 32-bit ops; WIDE = true is the same kernel with
 // 64-bit offsets for images of 4 GiB and more.
-template <int MODE, bool WIDE>
+// PITCHED = true adds blockIdx.z * pitch for batches whose images are not back to back (batches
+// that ARE back to back are launched as one tall image, so the common case pays nothing).
+template <int MODE, bool WIDE, bool PITCHED>
 __global__ void __launch_bounds__(256, MODE == 2 ? 6 : 8) encode_direct_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
@@ -74,27 +76,33 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 6 : 8) encode_direct_kernel(c
     if (bx >= P.bw || by >= P.bh) return;
 
     typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type off_t;
-    const uint8_t* img = P.src + (uint64_t)blockIdx.z * P.srcPitch;
     const off_t o0 = (off_t)by * (off_t)(4u * P.stride) + (off_t)(bx * 16u);
     const off_t o1 = o0 + P.stride, o2 = o1 + P.stride, o3 = o2 + P.stride;
-    const uint4 r0 = load_row(img + o0);
-    const uint4 r1 = load_row(img + o1);
-    const uint4 r2 = load_row(img + o2);
-    const uint4 r3 = load_row(img + o3);
+    const uint8_t* src = P.src;
+    uint8_t* dst = P.dst;
+    uint8_t* dst2 = P.dst2;
+    if (PITCHED) {
+        src += (uint64_t)blockIdx.z * P.srcPitch;
+        dst += (uint64_t)blockIdx.z * P.dstPitch;
+        if (MODE == kDual) dst2 += (uint64_t)blockIdx.z * P.dstPitch;
+    }
+    const uint4 r0 = load_row(src + o0);
+    const uint4 r1 = load_row(src + o1);
+    const uint4 r2 = load_row(src + o2);
+    const uint4 r3 = load_row(src + o3);
     const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
                             r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
 
     const off_t o = ((off_t)by * P.bw + bx) * 8u;
-    const uint64_t imgOut = (uint64_t)blockIdx.z * P.dstPitch;
     const BlockFront f = analyse(p);
     uint32_t w0, w1;
     if (MODE == kDxt1 || MODE == kDual) {
         encode_dxt1(p, f, w0, w1);
-        store_block(P.dst + imgOut + o, w0, w1);
+        store_block(dst + o, w0, w1);
     }
     if (MODE == kEtc1 || MODE == kDual) {
         encode_etc1(p, f, lut, w0, w1);
-        store_block((MODE == kDual ? P.dst2 : P.dst) + imgOut + o, w0, w1);
+        store_block((MODE == kDual ? dst2 : dst) + o, w0, w1);
     }
 }
 

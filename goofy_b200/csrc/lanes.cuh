@@ -46,6 +46,15 @@ GB_DEV uint32_t xor_and(uint32_t a, uint32_t b, uint32_t m)
     asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(r) : "r"(a), "r"(b), "r"(m));
     return r;
 }
+// ~(a | b) as ONE LOP3 (the compiler otherwise emits OR then NOT in front of a LEA.HI)
+GB_DEV uint32_t nor(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, 0, 0x03;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+// per-lane clamp(a + b, 0, c) on one signed 32-bit value
+GB_DEV int addclamp_s32(int a, int b, int c) { return __viaddmin_s32_relu(a, b, c); }
 
 #else  // host emulation (tests only)
 
@@ -88,6 +97,13 @@ GB_DEV uint32_t addclamp_s16x2(uint32_t a, uint32_t b, uint32_t c)
 }
 
 GB_DEV uint32_t xor_and(uint32_t a, uint32_t b, uint32_t m) { return (a ^ b) & m; }
+GB_DEV uint32_t nor(uint32_t a, uint32_t b) { return ~(a | b); }
+GB_DEV int addclamp_s32(int a, int b, int c)
+{
+    int v = a + b;
+    v = v > c ? c : v;
+    return v < 0 ? 0 : v;
+}
 
 #endif
 

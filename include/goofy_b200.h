@@ -69,6 +69,17 @@ const char* goofy_b200_error_string(int code);
 /* Kernels launched by this library in the calling process so far (all threads, all devices). */
 uint64_t goofy_b200_kernel_launches(void);
 
+/* Image load layer used by the uniform device entry points (process-wide):
+ *   AUTO    the library picks per shape (default)
+ *   DIRECT  one thread per block, four coalesced 128-bit global loads
+ *   TMA     2D tensor-map tiles staged in shared memory by persistent CTAs
+ * Both produce identical bytes.  set returns the previous setting (or GOOFY_B200_E_ARGS). */
+#define GOOFY_B200_LOAD_AUTO 0
+#define GOOFY_B200_LOAD_DIRECT 1
+#define GOOFY_B200_LOAD_TMA 2
+int goofy_b200_set_load_path(int path);
+int goofy_b200_get_load_path(void);
+
 /* ---- drop-in host-pointer API: same arguments, order and return codes as the reference ---- */
 int goofy_b200_compress_dxt1(unsigned char* result, const unsigned char* input, unsigned int width,
                              unsigned int height, unsigned int stride);

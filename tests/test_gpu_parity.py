@@ -238,3 +238,74 @@ def test_full_size_8192_properties(codec, oracle, reference):
     p = __import__("oracle.oracle", fromlist=["psnr_from_sse"]).psnr_from_sse(oracle.sse_rgb(dec, host[: size * band * 4]), size * band)
     # (the synthetic texture carries independent per-channel noise, which ETC1s' single base colour cannot follow)
     assert (30.0 if codec == DXT1 else 24.0) < p["psnr_rgb768"] < 60.0
+
+
+@pytest.fixture
+def tma_path():
+    prev = gb.set_load_path(gb.LOAD_TMA)
+    yield
+    gb.set_load_path(prev)
+
+
+@pytest.mark.parametrize("codec", CODECS)
+@pytest.mark.parametrize("shape", [(16, 4), (64, 8), (1024, 4), (1040, 12), (2048, 64), (3088, 20), (4096, 516), (272, 1028)])
+def test_tma_tile_path_shapes(codec, shape, oracle, tma_path):
+    """The TMA 2D-tile load layer (persistent CTAs, mbarrier ring) produces the same bytes as the oracle,
+    including widths that are not a multiple of the 1024-pixel tile (hardware zero-fill of the ragged edge)."""
+    w, h = shape
+    img = splitmix_rgba(w * h, seed=w * 7 + h)
+    launches = gb.kernel_launches()
+    rc, got = gpu_device(codec, img, w, h)
+    assert rc == 0 and gb.kernel_launches() == launches + 1
+    assert np.array_equal(got, oracle.compress(codec, img, w, h)[1])
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_tma_tile_path_padded_stride_batch_and_dual(codec, oracle, tma_path):
+    n, w, h, pad = 7, 1296, 36, 256
+    stride = w * 4 + pad
+    pitch = stride * h + 4096
+    buf = np.full(n * pitch, 0xAB, dtype=np.uint8)
+    imgs = []
+    for i in range(n):
+        img = synth_family(i % 4, w, h, seed=40 + i)
+        imgs.append(img)
+        view = buf[i * pitch: i * pitch + stride * h].reshape(h, stride)
+        view[:, : w * 4] = img.reshape(h, w * 4)
+    d_src = dev(buf)
+    out_pitch = w * h // 2 + 64
+    d_dst = torch.zeros(n * out_pitch, dtype=torch.uint8, device="cuda")
+    assert gb.encode_batch_uniform_device(codec, d_dst, d_src, w, h, stride, pitch, out_pitch, n) == 0
+    torch.cuda.synchronize()
+    got = d_dst.cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(got[i * out_pitch: i * out_pitch + w * h // 2], oracle.compress(codec, imgs[i], w, h)[1]), i
+        assert not got[i * out_pitch + w * h // 2: (i + 1) * out_pitch].any()
+    if codec == DXT1:
+        d_a = torch.zeros(n * out_pitch, dtype=torch.uint8, device="cuda")
+        d_b = torch.zeros(n * out_pitch, dtype=torch.uint8, device="cuda")
+        assert gb.encode_dual_device(d_a, d_b, d_src, w, h, stride, pitch, out_pitch, n) == 0
+        torch.cuda.synchronize()
+        for i in range(n):
+            assert np.array_equal(d_a.cpu().numpy()[i * out_pitch: i * out_pitch + w * h // 2], oracle.compress(DXT1, imgs[i], w, h)[1])
+            assert np.array_equal(d_b.cpu().numpy()[i * out_pitch: i * out_pitch + w * h // 2], oracle.compress(ETC1, imgs[i], w, h)[1])
+
+
+def test_tma_and_direct_agree_on_a_large_texture():
+    size = 4096
+    src = torch.empty((size, size, 4), dtype=torch.uint8, device="cuda")
+    from bench import fill_texture_device
+    fill_texture_device(torch, src, seed=11)
+    outs = {}
+    for path in (gb.LOAD_DIRECT, gb.LOAD_TMA):
+        prev = gb.set_load_path(path)
+        try:
+            for codec in CODECS:
+                d = torch.zeros(size * size // 2, dtype=torch.uint8, device="cuda")
+                assert gb.encode_device(codec, d, src, size, size, size * 4) == 0
+                torch.cuda.synchronize()
+                outs[(path, codec)] = d
+        finally:
+            gb.set_load_path(prev)
+    for codec in CODECS:
+        assert torch.equal(outs[(gb.LOAD_DIRECT, codec)], outs[(gb.LOAD_TMA, codec)])
