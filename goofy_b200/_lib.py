@@ -54,13 +54,19 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    import os
+
     from . import build as _build
 
-    if _build.needs_build():
+    path = LIB_PATH
+    override = os.environ.get("GOOFY_B200_LIB")  # experiments only: another build of the same sources
+    if override:
+        path = Path(override)
+    elif _build.needs_build():
         _build.build_library()
-    if not LIB_PATH.exists():
-        raise ImportError(f"{LIB_PATH} is missing: the CUDA library is the only implementation (no CPU fallback)")
-    lib = C.CDLL(str(LIB_PATH))
+    if not path.exists():
+        raise ImportError(f"{path} is missing: the CUDA library is the only implementation (no CPU fallback)")
+    lib = C.CDLL(str(path))
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library drift: fail loudly
         fn.restype = res

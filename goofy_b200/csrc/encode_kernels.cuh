@@ -43,7 +43,10 @@ __global__ void fill_control_lut_kernel()
 __device__ __forceinline__ uint4 load_row(const uint8_t* p)
 {
     uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+#ifndef GB_LOAD_PTX
+#define GB_LOAD_PTX "ld.global.nc.v4.u32"
+#endif
+    asm volatile(GB_LOAD_PTX " {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "l"(p));
     return v;
@@ -51,7 +54,10 @@ __device__ __forceinline__ uint4 load_row(const uint8_t* p)
 
 __device__ __forceinline__ void store_block(uint8_t* p, uint32_t w0, uint32_t w1)
 {
-    asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(w0), "r"(w1) : "memory");
+#ifndef GB_STORE_PTX
+#define GB_STORE_PTX "st.global.cs.v2.u32"
+#endif
+    asm volatile(GB_STORE_PTX " [%0], {%1,%2};" ::"l"(p), "r"(w0), "r"(w1) : "memory");
 }
 
 // 8 resident CTAs per SM (32 registers) for the single-codec kernels, 6 for the dual-output one.
