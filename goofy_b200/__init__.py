@@ -11,12 +11,12 @@ from .api import (DXT1, ETC1, CODEC_NAMES, GoofyError, check, compressDXT1, comp
                   encode_batch_device, encode_batch_sharded, encode_batch_uniform_device, encode_device,
                   encode_dual_device, encode_host, encode_sharded_host, error_string, kernel_launches,
                   make_descriptors, output_bytes, strip_partition, set_load_path, get_load_path, LOAD_AUTO,
-                  LOAD_DIRECT, LOAD_TMA)
+                  LOAD_DIRECT, LOAD_TMA, LOAD_ONESHOT)
 
 __all__ = [
     "DXT1", "ETC1", "CODEC_NAMES", "GoofyError", "check", "compressDXT1", "compressETC1", "device_count",
     "encode_batch_device", "encode_batch_sharded", "encode_batch_uniform_device", "encode_device",
     "encode_dual_device", "encode_host", "encode_sharded_host", "error_string", "kernel_launches",
     "make_descriptors", "output_bytes", "strip_partition", "set_load_path", "get_load_path", "LOAD_AUTO",
-    "LOAD_DIRECT", "LOAD_TMA",
+    "LOAD_DIRECT", "LOAD_TMA", "LOAD_ONESHOT",
 ]

@@ -43,7 +43,7 @@ def kernel_launches() -> int:
     return int(_lib.load().goofy_b200_kernel_launches())
 
 
-LOAD_AUTO, LOAD_DIRECT, LOAD_TMA = 0, 1, 2
+LOAD_AUTO, LOAD_DIRECT, LOAD_TMA, LOAD_ONESHOT = 0, 1, 2, 3
 
 
 def set_load_path(path: int) -> int:

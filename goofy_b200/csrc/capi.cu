@@ -33,6 +33,8 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? GOOFY_B200_OK : GO
         if (e__ != cudaSuccess) return cuda_rc(e__);    \
     } while (0)
 
+std::atomic<int> g_loadPath{GOOFY_B200_LOAD_AUTO};
+
 // ---- per-device one-time state: the ETC1 control table in device memory ----
 constexpr int kMaxDevices = 64;
 std::once_flag g_lutOnce[kMaxDevices];
@@ -84,8 +86,44 @@ int launch_direct_grid(const gb::EncodeParams& Q, dim3 grid, dim3 block, cudaStr
     return cuda_rc(cudaGetLastError());
 }
 
+int sm_count(int dev);
+
+// Persistent row-walking launch for one (possibly very tall) image.
 template <int MODE>
-int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream)
+int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
+{
+    uint32_t tx = 32u;
+    while (tx < 256u && tx < P.bw) tx <<= 1;
+    const uint32_t ty = 256u / tx;
+    const uint32_t gx = (P.bw + tx - 1u) / tx;
+    const uint32_t rowGroups = (P.bh + ty - 1u) / ty;
+    const int sms = sm_count(dev);
+    if (sms <= 0) return GOOFY_B200_E_DEVICE;
+    static const bool prefetch = getenv("GOOFY_B200_ROWS_PREFETCH") != nullptr;  // experiment switch
+    const uint32_t resident = (uint32_t)sms * (prefetch ? 5u : (MODE == gb::kDual ? 6u : 8u));
+    // CTAs walk ~3.5 block rows each on an 8192^2 texture: enough to amortise the per-thread set-up,
+    // few enough that CTAs keep retiring and restarting at staggered times (measured: 1x resident
+    // 5634, 4x 6111, 14x 5640 GB/s for ETC1s; profiles/r01_rows_grid_sweep.txt).
+    static const uint32_t gyMult = []() { const char* e = getenv("GOOFY_B200_ROWS_GY_MULT"); const int v = e ? atoi(e) : 4; return v > 0 ? (uint32_t)v : 4u; }();
+    uint32_t gy = (uint32_t)(((uint64_t)resident * gyMult) / gx);
+    if (gy == 0u) gy = 1u;
+    if (gy > rowGroups) gy = rowGroups;
+    if (gy > 65535u) gy = 65535u;
+    const dim3 grid(gx, gy, 1), block(tx, ty, 1);
+    const bool narrow = (uint64_t)P.bh * 4u * P.stride + (uint64_t)P.bw * 16u < 0xFFFFFFFFull;
+    if (prefetch) {
+        if (narrow) gb::encode_rows_prefetch_kernel<MODE, false><<<grid, block, 0, stream>>>(P);
+        else gb::encode_rows_prefetch_kernel<MODE, true><<<grid, block, 0, stream>>>(P);
+    } else {
+        if (narrow) gb::encode_rows_kernel<MODE, false><<<grid, block, 0, stream>>>(P);
+        else gb::encode_rows_kernel<MODE, true><<<grid, block, 0, stream>>>(P);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
+template <int MODE>
+int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream, int dev)
 {
     // A batch whose images lie back to back (pitch == image size) is one tall image.
     const uint64_t imageBytes = (uint64_t)P.bh * 4u * P.stride, outBytes = (uint64_t)P.bh * P.bw * 8u;
@@ -93,7 +131,13 @@ int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream)
         P.bh *= nImages;
         nImages = 1u;
     }
-    // threads: x walks blocks along a row (coalescing), y stacks block rows for narrow images
+    // Load-path policy for AUTO: the DXT1 kernel is HBM-bound either way and
+    // one-shot CTAs are marginally faster (6617 vs 6598 GB/s); the ETC1s and dual-output kernels are
+    // instruction-bound and gain 4-13 % from row-walking CTAs.
+    const int path = g_loadPath.load(std::memory_order_relaxed);
+    const bool rows = path == GOOFY_B200_LOAD_DIRECT || (path == GOOFY_B200_LOAD_AUTO && MODE != gb::kDxt1);
+    if (nImages == 1u && rows) return launch_rows<MODE>(P, stream, dev);
+    // one-shot CTAs (pitched batches): threads: x walks blocks along a row (coalescing), y stacks block rows for narrow images
     // (x is a power of two and x*y == 256: the kernels rely on exactly 256 threads)
     uint32_t tx = 32u;
     while (tx < 256u && tx < P.bw) tx <<= 1;
@@ -120,7 +164,6 @@ int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream)
 }
 
 // ---------------------------------------------------------------- TMA tile path
-std::atomic<int> g_loadPath{GOOFY_B200_LOAD_AUTO};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -145,6 +188,19 @@ struct DeviceInfo {
     int smCount = 0;
     int tmaCtasPerSm[3] = {0, 0, 0};  // 0 = not yet configured
 };
+DeviceInfo g_devInfo[kMaxDevices];
+std::mutex g_devInfoMutex;
+
+int sm_count(int dev)
+{
+    std::lock_guard<std::mutex> g(g_devInfoMutex);
+    DeviceInfo& di = g_devInfo[dev];
+    if (di.smCount == 0 && cudaDeviceGetAttribute(&di.smCount, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        cudaGetLastError();
+        di.smCount = 0;
+    }
+    return di.smCount;
+}
 
 // Depth of the tile ring.  GOOFY_B200_TMA_STAGES overrides it for experiments (2..8).
 uint32_t tma_stages()
@@ -156,9 +212,6 @@ uint32_t tma_stages()
     }();
     return n;
 }
-DeviceInfo g_devInfo[kMaxDevices];
-std::mutex g_devInfoMutex;
-
 gb::FastDiv make_fastdiv(uint32_t d)
 {
     gb::FastDiv f;
@@ -274,9 +327,9 @@ int encode_uniform(int mode, void* dst, void* dst2, const void* src, uint32_t wi
     P.srcPitch = srcPitch;
     P.dstPitch = dstPitch;
     switch (mode) {
-        case gb::kDxt1: return launch_direct<gb::kDxt1>(P, nImages, stream);
-        case gb::kEtc1: return launch_direct<gb::kEtc1>(P, nImages, stream);
-        case gb::kDual: return launch_direct<gb::kDual>(P, nImages, stream);
+        case gb::kDxt1: return launch_direct<gb::kDxt1>(P, nImages, stream, dev);
+        case gb::kEtc1: return launch_direct<gb::kEtc1>(P, nImages, stream, dev);
+        case gb::kDual: return launch_direct<gb::kDual>(P, nImages, stream, dev);
         default: return GOOFY_B200_E_CODEC;
     }
 }
@@ -556,7 +609,7 @@ uint64_t goofy_b200_kernel_launches(void) { return g_launches.load(std::memory_o
 
 int goofy_b200_set_load_path(int path)
 {
-    if (path < GOOFY_B200_LOAD_AUTO || path > GOOFY_B200_LOAD_TMA) return GOOFY_B200_E_ARGS;
+    if (path < GOOFY_B200_LOAD_AUTO || path > GOOFY_B200_LOAD_ONESHOT) return GOOFY_B200_E_ARGS;
     return g_loadPath.exchange(path, std::memory_order_relaxed);
 }
 

@@ -71,12 +71,13 @@ uint64_t goofy_b200_kernel_launches(void);
 
 /* Image load layer used by the uniform device entry points (process-wide):
  *   AUTO    the library picks per shape (default)
- *   DIRECT  one thread per block, four coalesced 128-bit global loads
+ *   DIRECT  one thread per block, four coalesced 128-bit global loads, persistent CTAs walking down the image
  *   TMA     2D tensor-map tiles staged in shared memory by persistent CTAs
  * Both produce identical bytes.  set returns the previous setting (or GOOFY_B200_E_ARGS). */
 #define GOOFY_B200_LOAD_AUTO 0
 #define GOOFY_B200_LOAD_DIRECT 1
 #define GOOFY_B200_LOAD_TMA 2
+#define GOOFY_B200_LOAD_ONESHOT 3 /* DIRECT with one-shot CTAs instead of persistent row-walking CTAs */
 int goofy_b200_set_load_path(int path);
 int goofy_b200_get_load_path(void);
 
