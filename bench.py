@@ -34,8 +34,8 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--codec", choices=["dxt1", "etc1"], default="dxt1")
     ap.add_argument("--size", type=int, default=8192, help="texture width = height")
@@ -63,57 +63,80 @@ def hbm_peak():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    """Samples SM clock, power and throttle reasons of one GPU while the timed region runs.
+    NVML (nvidia_ml_py) every 2 ms in a thread -- the timed region of this bench lasts tens of
+    milliseconds, too short for `nvidia-smi -lms 200`; nvidia-smi is the fallback."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+        self.samples = []
+        self.stop_flag = threading.Event()
         self.thread = None
+        self.nvml = None
+        self.handle = None
+        self.sm_max = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
-            return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except (ValueError, IndexError):
+                    idx = self.gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+        self.thread = threading.Thread(target=self._run_nvml if self.nvml else self._run_smi, daemon=True)
         self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run_nvml(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _run_smi(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.sm_max = float(out[1])
+                self.samples.append((float(out[0]), float(out[2]), int(out[3].strip(), 16)))
+            except Exception:
+                return
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smmax, power, reasons = [], [], [], set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
-            try:
-                sm.append(float(r[1])); smmax.append(float(r[2])); power.append(float(r[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smmax)), "power_w_max": float(max(power)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
+        sm = [x[0] for x in self.samples]
+        bits = 0
+        for x in self.samples:
+            bits |= x[2]
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": self.sm_max,
+                "power_w_max": float(max(x[1] for x in self.samples)), "samples": len(sm),
+                "source": "nvml" if self.nvml else "nvidia-smi",
+                "reasons": [name for name, bit in self.REASONS if bits & bit]}
 
 
 # ----------------------------------------------------------------------------- synthetic input
@@ -239,8 +262,14 @@ def run_b200_arm(args):
         fill_texture_device(torch, src[b], seed=1000 * rank + b)
     torch.cuda.synchronize()
 
+    img_bytes = size * size * 4
+
     def step(c=codec):
-        # one launch per texture: the launch a caller of the device API makes for one 8192^2 texture
+        # one pass over the batch through the batched device-resident entry point (one launch)
+        gb.check(gb.encode_batch_uniform_device(c, dst, src, size, size, stride, img_bytes, out_bytes, batch))
+
+    def step_per_texture(c=codec):
+        # the same batch as one call (and one launch) per 8192^2 texture
         for b in range(batch):
             gb.check(gb.encode_device(c, dst[b], src[b], size, size, stride))
 
@@ -249,10 +278,12 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
             fn()
         barrier()
+        if sampler is not None:
+            sampler.start()      # clocks are sampled during the timed region only
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = gb.kernel_launches()
         e0.record()
@@ -268,32 +299,37 @@ def run_b200_arm(args):
             ms = float(t.item())
         return ms, launches
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms, launches = timed(step, args.steps, args.warmup)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, launches = timed(step, args.steps, args.warmup, sampler)
     clocks = sampler.stop() if rank == 0 else None
 
     total_px = px_per_step * args.steps * world
     value = total_px / (ms * 1e-3) / 1e6
-    launch_ms = ms / (args.steps * batch)
-    achieved = size * size * BYTES_PER_PIXEL / (launch_ms * 1e-3) / 1e9
+    launches_per_step = launches / args.steps
+    launch_ms = ms / launches
+    bytes_per_launch = px_per_step * BYTES_PER_PIXEL / launches_per_step
+    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = hbm_peak()
+
+    # same batch, one launch per texture (what a caller encoding single 8192^2 textures sees)
+    side_steps = max(min(args.steps // 2, 100), 3)
+    ms_s, launches_s = timed(step_per_texture, side_steps, 3)
+    value_s = px_per_step * side_steps * world / (ms_s * 1e-3) / 1e6
 
     # the other codec, same protocol (BASELINE.json's metric names both)
     other = gb.ETC1 if codec == gb.DXT1 else gb.DXT1
-    ms_o, _ = timed(lambda: step(other), max(args.steps // 2, 3), 3)
-    value_o = px_per_step * max(args.steps // 2, 3) * world / (ms_o * 1e-3) / 1e6
+    side_steps = max(min(args.steps // 2, 100), 3)
+    ms_o, _ = timed(lambda: step(other), side_steps, 3)
+    value_o = px_per_step * side_steps * world / (ms_o * 1e-3) / 1e6
     achieved_o = value_o / world * 1e6 * BYTES_PER_PIXEL / 1e9
 
     # dual-output pass: both codecs from one read (5 B/px)
     dst2 = torch.empty((batch, out_bytes), dtype=torch.uint8, device=dev)
 
     def dual_step():
-        for b in range(batch):
-            gb.check(gb.encode_dual_device(dst[b], dst2[b], src[b], size, size, stride))
-    ms_d, _ = timed(dual_step, max(args.steps // 2, 3), 3)
-    value_d = px_per_step * max(args.steps // 2, 3) * world / (ms_d * 1e-3) / 1e6
+        gb.check(gb.encode_dual_device(dst, dst2, src, size, size, stride, img_bytes, out_bytes, batch))
+    ms_d, _ = timed(dual_step, side_steps, 3)
+    value_d = px_per_step * side_steps * world / (ms_d * 1e-3) / 1e6
 
     # ---- end to end through the drop-in host API: pinned host buffers, H2D + D2H inside the timed region
     e2e = None
@@ -348,16 +384,22 @@ def run_b200_arm(args):
                                    f"(BASELINE.json configs[{1 if args.codec == 'dxt1' else 2}])",
                        "codec": args.codec, "texture": [size, size], "textures_per_step": batch,
                        "pixels_per_step_per_gpu": px_per_step, "stride": stride,
-                       "l2": f"inputs larger than L2: {batch} distinct {size * size * 4 >> 20} MiB textures rotate, "
-                             f"each launch streams {int(size * size * BYTES_PER_PIXEL) >> 20} MiB",
+                       "l2": f"inputs larger than L2: every step streams {batch} distinct {size * size * 4 >> 20} MiB textures "
+                             f"({int(px_per_step * BYTES_PER_PIXEL) >> 20} MiB per step vs 126 MB of L2)",
                        "load_path": args.load_path,
                        "sharding": "one batch per rank, no collectives" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "kernel": f"encode_direct_kernel<{args.codec}>", "bytes_per_launch": size * size * BYTES_PER_PIXEL,
-                         "launch_ms": launch_ms},
+                         "kernel": ("encode_direct_kernel" if codec == gb.DXT1 and args.load_path in ("auto", "oneshot")
+                                    else "encode_tma_kernel" if args.load_path == "tma" else "encode_rows_kernel") + f"<{args.codec}>",
+                         "bytes_per_launch": bytes_per_launch, "launch_ms": launch_ms,
+                         "like_for_like_ceiling": "tools/membench rows4/nc: 6696 GB/s for an 8:1 read:write stream at 302 MB per launch "
+                                                  "(profiles/r01_membench.txt)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "per_texture_launch": {"value": value_s, "unit": "MP/s", "launches_per_step": launches_s / side_steps,
+                                   "achieved_gbs_per_gpu": value_s / world * 1e6 * BYTES_PER_PIXEL / 1e9,
+                                   "note": "same batch, one goofy_b200_encode_device call per texture"},
             "other_codec": {"codec": "etc1" if codec == gb.DXT1 else "dxt1", "value": value_o, "unit": "MP/s",
                             "achieved_gbs_per_gpu": achieved_o, "frac": achieved_o / peak},
             "dual_output": {"value": value_d, "unit": "MP/s (each pixel encoded to both DXT1 and ETC1s)",
@@ -375,9 +417,23 @@ def run_b200_arm(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        return run_reference_arm(args)
-    return run_b200_arm(args)
+    # Keep stdout to the one JSON line: libraries (NCCL prints its version banner there) get stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
+    real_print = print
+
+    def print_json(*a, **k):
+        real_print(*a, **k, file=json_out, flush=True)
+    globals()["print"] = print_json
+    try:
+        if args.impl == "reference":
+            return run_reference_arm(args)
+        return run_b200_arm(args)
+    finally:
+        globals()["print"] = real_print
+        json_out.flush()
 
 
 if __name__ == "__main__":

@@ -40,6 +40,8 @@ PROTOTYPES = {
     "goofy_b200_encode_device": (_int, [_int, _vp, _vp, _u32, _u32, _u32, _vp]),
     "goofy_b200_encode_batch_uniform_device": (_int, [_int, _vp, _vp, _u32, _u32, _u32, _u64, _u64, _u32, _vp]),
     "goofy_b200_encode_dual_device": (_int, [_vp, _vp, _vp, _u32, _u32, _u32, _u64, _u64, _u32, _vp]),
+    "goofy_b200_decode_device": (_int, [_int, _vp, _vp, _u32, _u32, _u32, _vp]),
+    "goofy_b200_block_sse_device": (_int, [_int, _vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     "goofy_b200_encode_batch_device": (_int, [_int, C.POINTER(GoofyB200Image), _u32, _vp]),
     "goofy_b200_encode_batch_sharded": (_int, [_int, C.POINTER(GoofyB200Image), _u32]),
     "goofy_b200_encode_sharded_host": (_int, [_int, _vp, _vp, _u32, _u32, _u32, _int]),

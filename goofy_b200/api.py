@@ -147,6 +147,25 @@ def encode_dual_device(d_result_dxt1, d_result_etc1, d_input, width: int, height
         input_image_pitch, result_image_pitch, n_images, _stream_ptr(stream)))
 
 
+def decode_device(codec: int, d_rgba, d_blocks, width: int, height: int, stride: int, stream=None) -> int:
+    """BC1 / ETC1 blocks -> RGBA8 on the device (DecoderBC::decodeBlockDXT1/ETC1, Src/decoder.cpp:933-971)."""
+    return int(_lib.load().goofy_b200_decode_device(codec, _dev_ptr(d_rgba), _dev_ptr(d_blocks), width, height, stride,
+                                                    _stream_ptr(stream)))
+
+
+def block_sse_device(codec: int, d_blocks, d_rgba, width: int, height: int, stride: int, d_sse_rgb, stream=None) -> int:
+    """Adds per-channel sums of squared (decoded - source) to the 3 x uint64 device array d_sse_rgb."""
+    return int(_lib.load().goofy_b200_block_sse_device(codec, _dev_ptr(d_blocks), _dev_ptr(d_rgba), width, height, stride,
+                                                       _dev_ptr(d_sse_rgb), _stream_ptr(stream)))
+
+
+def psnr_rgb768(sse_rgb, pixels: int) -> float:
+    """The reference harness's RGB-PSNR (Src/main.cpp:444,466): peak 768 over the SUM of channel MSEs."""
+    import math
+    mse = float(sum(int(v) for v in sse_rgb)) / pixels
+    return float("inf") if mse < 1e-7 else 10.0 * math.log10(768.0 * 768.0 / mse)
+
+
 def make_descriptors(images: Iterable[Sequence]) -> C.Array:
     """images: iterable of (d_src, d_dst, width, height, stride[, device]) -> GoofyB200Image[n]."""
     items = list(images)

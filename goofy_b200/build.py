@@ -10,7 +10,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libgoofy_b200.so"
 SOURCES = [CSRC / "capi.cu"]
-HEADERS = [CSRC / "lanes.cuh", CSRC / "block_codec.cuh", CSRC / "encode_kernels.cuh", CSRC / "tma_kernels.cuh",
+HEADERS = [CSRC / "lanes.cuh", CSRC / "block_codec.cuh", CSRC / "encode_kernels.cuh", CSRC / "tma_kernels.cuh", CSRC / "decode_kernels.cuh",
            PKG_DIR.parent / "include" / "goofy_b200.h"]
 
 NVCC_FLAGS = [

@@ -20,6 +20,7 @@
 #include "../../include/goofy_b200.h"
 #include "encode_kernels.cuh"
 #include "tma_kernels.cuh"
+#include "decode_kernels.cuh"
 
 namespace {
 
@@ -672,6 +673,64 @@ int goofy_b200_encode_dual_device(void* d_result_dxt1, void* d_result_etc1, cons
 {
     return encode_uniform(gb::kDual, d_result_dxt1, d_result_etc1, d_input, width, height, stride, input_image_pitch,
                           result_image_pitch, n_images, (cudaStream_t)stream);
+}
+
+int goofy_b200_decode_device(int codec, void* d_rgba, const void* d_blocks, uint32_t width, uint32_t height, uint32_t stride,
+                             void* stream)
+{
+    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
+    if (width % 4u != 0u) return GOOFY_B200_E_WIDTH;
+    if (height % 4u != 0u) return GOOFY_B200_E_HEIGHT;
+    if (width == 0u || height == 0u) return GOOFY_B200_OK;
+    if ((uint64_t)stride < (uint64_t)width * 4u) return GOOFY_B200_E_STRIDE;
+    if (!d_rgba || !d_blocks) return GOOFY_B200_E_NULL;
+    if (((uintptr_t)d_rgba & 15u) != 0u || (stride & 15u) != 0u || ((uintptr_t)d_blocks & 7u) != 0u) return GOOFY_B200_E_ALIGN;
+    if (height / 4u > 65535u) return GOOFY_B200_E_ARGS;
+    int rc = ensure_device_ready();
+    if (rc != GOOFY_B200_OK) return rc;
+    gb::DecodeParams P;
+    P.blocks = (const uint8_t*)d_blocks;
+    P.rgba = (uint8_t*)d_rgba;
+    P.source = nullptr;
+    P.sse = nullptr;
+    P.bw = width / 4u;
+    P.bh = height / 4u;
+    P.stride = stride;
+    const dim3 grid((P.bw + 255u) / 256u, P.bh, 1);
+    if (codec == GOOFY_B200_DXT1) gb::decode_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    else gb::decode_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
+int goofy_b200_block_sse_device(int codec, const void* d_blocks, const void* d_rgba, uint32_t width, uint32_t height,
+                                uint32_t stride, uint64_t* d_sse_rgb, void* stream)
+{
+    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
+    if (width % 4u != 0u) return GOOFY_B200_E_WIDTH;
+    if (height % 4u != 0u) return GOOFY_B200_E_HEIGHT;
+    if (width == 0u || height == 0u) return GOOFY_B200_OK;
+    if ((uint64_t)stride < (uint64_t)width * 4u) return GOOFY_B200_E_STRIDE;
+    if (!d_rgba || !d_blocks || !d_sse_rgb) return GOOFY_B200_E_NULL;
+    if (((uintptr_t)d_rgba & 15u) != 0u || (stride & 15u) != 0u || ((uintptr_t)d_blocks & 7u) != 0u ||
+        ((uintptr_t)d_sse_rgb & 7u) != 0u)
+        return GOOFY_B200_E_ALIGN;
+    if (height / 4u > 65535u) return GOOFY_B200_E_ARGS;
+    int rc = ensure_device_ready();
+    if (rc != GOOFY_B200_OK) return rc;
+    gb::DecodeParams P;
+    P.blocks = (const uint8_t*)d_blocks;
+    P.rgba = nullptr;
+    P.source = (const uint8_t*)d_rgba;
+    P.sse = (unsigned long long*)d_sse_rgb;
+    P.bw = width / 4u;
+    P.bh = height / 4u;
+    P.stride = stride;
+    const dim3 grid((P.bw + 255u) / 256u, P.bh, 1);
+    if (codec == GOOFY_B200_DXT1) gb::block_sse_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    else gb::block_sse_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
 }
 
 int goofy_b200_encode_batch_device(int codec, const GoofyB200Image* descs, uint32_t n_images, void* stream)

@@ -112,6 +112,17 @@ int goofy_b200_encode_dual_device(void* d_result_dxt1, void* d_result_etc1, cons
  * to the device on `stream`. */
 int goofy_b200_encode_batch_device(int codec, const GoofyB200Image* descs, uint32_t n_images, void* stream);
 
+/* ---- the step after the encoder (reference: Src/main.cpp:561-613 decode, :403-469 MSE/PSNR) ---- */
+/* Decode width*height/2 bytes of BC1 / ETC1 blocks into RGBA8 (alpha 255; BC1 3-colour
+ * "transparent" index writes 0,0,0,0).  width and height multiples of 4. */
+int goofy_b200_decode_device(int codec, void* d_rgba, const void* d_blocks, uint32_t width, uint32_t height,
+                             uint32_t stride, void* stream);
+/* Decode and compare with the source pixels without writing the decoded image: ADDS the sum of
+ * squared errors of the R, G and B channels to d_sse_rgb[0..2] (device uint64, caller zeroes).
+ * psnrRGB of the reference harness = 10*log10(768^2 / ((sse[0]+sse[1]+sse[2]) / pixels)). */
+int goofy_b200_block_sse_device(int codec, const void* d_blocks, const void* d_rgba, uint32_t width, uint32_t height,
+                                uint32_t stride, uint64_t* d_sse_rgb, void* stream);
+
 /* ---- multi-GPU shard scheduler (no collectives: blocks are independent) ---- */
 /* Images may live on different devices (descs[i].device >= 0 required).  Work is grouped per
  * device, launched from one host thread per device, and all devices are synchronised

@@ -309,3 +309,52 @@ def test_tma_and_direct_agree_on_a_large_texture():
             gb.set_load_path(prev)
     for codec in CODECS:
         assert torch.equal(outs[(gb.LOAD_DIRECT, codec)], outs[(gb.LOAD_TMA, codec)])
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_gpu_decoder_and_sse_match_oracle(codec, oracle):
+    """Row N2 of SURVEY.md 8(f): BC1 / ETC1 decode and the squared-error reduction on the device,
+    against the oracle decoder (itself checked against Src/decoder.cpp in tests/test_oracle.py)."""
+    w, h = 512, 256
+    img = synth_family(1, w, h)
+    blocks = oracle.compress(codec, img, w, h)[1]
+    d_blocks, d_src = dev(blocks), dev(img)
+    d_out = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    assert gb.decode_device(codec, d_out, d_blocks, w, h, w * 4) == 0
+    torch.cuda.synchronize()
+    want = oracle.decode(codec, blocks, w, h)
+    assert np.array_equal(d_out.cpu().numpy(), want)
+    d_sse = torch.zeros(3, dtype=torch.int64, device="cuda")
+    assert gb.block_sse_device(codec, d_blocks, d_src, w, h, w * 4, d_sse) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sse.cpu().numpy().astype(np.float64), oracle.sse_rgb(want, img))
+    # arbitrary blocks (all BC1 modes; ETC1 individual + differential without overflow, both flips)
+    rnd = splitmix_rgba(w * h // 8, seed=99).reshape(-1, 8).copy()
+    if codec == ETC1:
+        diff = (rnd[:, 3] & 2) != 0
+        rnd[diff, 0:3] &= 0xF8
+    rnd = rnd.reshape(-1)
+    assert gb.decode_device(codec, d_out, dev(rnd), w, h, w * 4) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), oracle.decode(codec, rnd, w, h))
+
+
+def test_gpu_psnr_of_test_images_matches_reference_numbers(oracle):
+    """Encode -> decode -> PSNR entirely on the device; Kodak means measured with the reference's own
+    decoder are 37.218 (DXT1) / 36.519 (ETC1s) dB."""
+    names = [n for n in image_names() if n.startswith("kodim")]
+    if len(names) != 24:
+        pytest.skip("Kodak images not present")
+    for codec, want in ((DXT1, 37.218), (ETC1, 36.519)):
+        vals = []
+        for n in names:
+            img = load_test_image(n)
+            h, w = img.shape[:2]
+            d_src = dev(img)
+            d_blk = torch.zeros(w * h // 2, dtype=torch.uint8, device="cuda")
+            d_sse = torch.zeros(3, dtype=torch.int64, device="cuda")
+            assert gb.encode_device(codec, d_blk, d_src, w, h, w * 4) == 0
+            assert gb.block_sse_device(codec, d_blk, d_src, w, h, w * 4, d_sse) == 0
+            torch.cuda.synchronize()
+            vals.append(gb.psnr_rgb768(d_sse.cpu().tolist(), w * h))
+        assert abs(float(np.mean(vals)) - want) < 0.01, (codec, np.mean(vals))
