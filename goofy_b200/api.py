@@ -22,7 +22,10 @@ from ._lib import GoofyB200Image
 
 DXT1 = 0
 ETC1 = 1
-CODEC_NAMES = {DXT1: "dxt1", ETC1: "etc1"}
+# bit-exact with goofyRef:: (Src/goofy_tc_reference.cpp) instead of with the SSE2 path
+DXT1_FLOATREF = 16
+ETC1_FLOATREF = 17
+CODEC_NAMES = {DXT1: "dxt1", ETC1: "etc1", DXT1_FLOATREF: "dxt1_floatref", ETC1_FLOATREF: "etc1_floatref"}
 
 
 class GoofyError(RuntimeError):
@@ -112,6 +115,20 @@ def compressETC1(result, input, width: int, height: int, stride: int) -> int:
     """goofy::compressETC1 (GoofyTC/goofy_tc.h:1528)."""
     return int(_lib.load().goofy_b200_compress_etc1(_host_ptr(result, True), _host_ptr(input, False),
                                                     width, height, stride))
+
+
+class goofyRef:
+    """Mirror of namespace goofyRef (Src/goofy_tc_reference.h:5-9): the float-reference flavour."""
+
+    @staticmethod
+    def compressDXT1(result, input, width: int, height: int, stride: int) -> int:
+        return int(_lib.load().goofy_b200_compress_dxt1_floatref(_host_ptr(result, True), _host_ptr(input, False),
+                                                                 width, height, stride))
+
+    @staticmethod
+    def compressETC1(result, input, width: int, height: int, stride: int) -> int:
+        return int(_lib.load().goofy_b200_compress_etc1_floatref(_host_ptr(result, True), _host_ptr(input, False),
+                                                                 width, height, stride))
 
 
 def encode_host(codec: int, result, input, width: int, height: int, stride: int) -> int:

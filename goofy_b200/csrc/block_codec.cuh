@@ -172,6 +172,115 @@ GB_DEV void encode_etc1(const uint32_t (&p)[16], const BlockFront& f, const uint
     word0 = (rb & 0x00F800F8u) | ((g & 0xF8u) << 8) | controlLut[f.range];
 }
 
+// ======================================================================== float-reference flavour
+// goofyRef::compressDXT1/ETC1 (Src/goofy_tc_reference.cpp:514-623 goofyCompressBlock, :634-670 DXT1
+// pack, :684-792 ETC1S pack) computes in float, but every value it forms is a multiple of 1/64 below
+// 2^15, so it is reproduced here EXACTLY in integers (and is therefore immune to FMA contraction):
+//   Y4 = R + 2G + B (= 4 * brightness)          range4 = max(maxY4 - minY4, 4 * minRange)
+//   mid8 = maxY4 + minY4 (= 8 * midPoint)       q = 0.375 * range  ->  Q = 3 * range4 (= 32 q)
+//   diff = Y - mid  ->  d = 8 * Y4 - 4 * mid8 (= 32 diff);   "diff > 0" <=> d >= 1;   "|diff| < q" <=> |d| < Q
+// Results differ from the SSE2 flavour by design; this flavour exists so
+// that "bit-exact against Src/goofy_tc_reference.cpp" can be met literally.
+constexpr uint32_t kLuma8 = 0x00081008u;  // dp4a weights 8R + 16G + 8B = 8 * Y4
+
+struct RefFront {
+    uint32_t mnG, mxG, mnRB, mxRB;  // same layout as BlockFront
+    uint32_t range4, mid8;
+    uint32_t laneBias, kLo, kHi;    // lane = d + 0x3FFF: bit 14 <=> d >= 1; bit 15 of (lane+kLo)^(lane+kHi) <=> |d| < Q
+};
+
+GB_DEV RefFront analyse_ref(const uint32_t (&p)[16], uint32_t minRange4)
+{
+    RefFront f;
+    uint32_t q[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) q[i] = p[i] << 8;
+    f.mnG = reduce16<false>(p);
+    f.mxG = reduce16<true>(p);
+    f.mnRB = reduce16<false>(q);
+    f.mxRB = reduce16<true>(q);
+    const uint32_t minY4 = dp4a(prmt(f.mnRB, f.mnG, 0x3351), kLuma, 0u);
+    const uint32_t maxY4 = dp4a(prmt(f.mxRB, f.mxG, 0x3351), kLuma, 0u);
+    const uint32_t spread = maxY4 - minY4;
+    f.range4 = spread > minRange4 ? spread : minRange4;   // :549
+    f.mid8 = maxY4 + minY4;                                // :551
+    const uint32_t Q = 3u * f.range4;                      // :554
+    f.laneBias = 0x3FFFu - 4u * f.mid8;
+    f.kLo = (0x4000u + Q) * 0x10001u;
+    f.kHi = (0x4001u - Q) * 0x10001u;
+    return f;
+}
+
+GB_DEV uint32_t ref_lanes_of(uint32_t a, uint32_t b, uint32_t laneBias)
+{
+    const uint32_t hi = dp4a(b, kLuma8, laneBias);
+    return dp4a(a, kLuma8, hi * 65536u + laneBias);
+}
+
+// :634-670  c0 = (R>>3)<<11 | (G>>3)<<6 | B>>3 | 0x20 from the max corner, c1 from the min corner
+GB_DEV void encode_dxt1_ref(const uint32_t (&p)[16], const RefFront& f, uint32_t& word0, uint32_t& word1)
+{
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t e = ref_lanes_of(p[i], p[i + 8], f.laneBias);
+        const uint32_t x = (e + f.kLo) ^ (e + f.kHi);
+        const uint32_t z = bitsel(x, ~e, 0x80008000u);  // bit15 = near, bit14 = !(diff > 0)
+        acc = bitsel(z, acc >> 2, 0xC000C000u);
+    }
+    word1 = acc;
+    const uint32_t rr = prmt(f.mxRB, f.mnRB, 0x5010);
+    const uint32_t bb = prmt(f.mxRB, f.mnRB, 0x7030);
+    const uint32_t gg = prmt(f.mxG, f.mnG, 0x5410);
+    const uint32_t rg = bitsel(rr, gg >> 5, 0xF800F800u);
+    word0 = (bitsel(rg, bb >> 11, 0xFFC0FFC0u) & 0xFFDFFFDFu) | 0x20u;
+}
+
+// :758-792  base colour = average colour moved onto the mid brightness, (v & 0xF8) packing,
+// control byte from floatToByte(range / 2) against {10,21,36,52,75,90,126} (`controlLut[brightRange]`).
+GB_DEV void encode_etc1_ref(const uint32_t (&p)[16], const RefFront& f, const uint32_t* controlLut, uint32_t& word0,
+                            uint32_t& word1)
+{
+    uint32_t accNeg = 0, accFar = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int y = k & 3, x = k >> 2;
+        const uint32_t e = ref_lanes_of(p[4 * y + 2 + x], p[4 * y + x], f.laneBias);
+        const uint32_t x2 = (e + f.kLo) ^ (e + f.kHi);
+        accNeg = bitsel(~e, accNeg >> 1, 0x40004000u);
+        accFar = bitsel(~x2, accFar >> 1, 0x80008000u);
+    }
+    word1 = prmt(accNeg >> 7, accFar >> 8, 0x6420);
+
+    uint32_t sumR = 0, sumG = 0, sumB = 0;  // :526-536 (avgColor * 16)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        sumR = dp4a(p[i], 0x00000001u, sumR);
+        sumG = dp4a(p[i], 0x00000100u, sumG);
+        sumB = dp4a(p[i], 0x00010000u, sumB);
+    }
+    // everything * 64: avg = sum * 4, avgY = sumR + 2 sumG + sumB, mid = mid8 * 8; floatToByte = floor(v + 0.5) clamped
+    const int diffY64 = (int)(8u * f.mid8) - (int)(sumR + 2u * sumG + sumB);   // :606-607
+    const int sums[3] = {(int)sumR, (int)sumG, (int)sumB};
+    uint32_t packed = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int v = (4 * sums[c] + diffY64 + 32) >> 6;   // arithmetic shift = floor; negative -> clamped to 0 below
+        v = v < 0 ? 0 : (v > 255 ? 255 : v);
+        packed |= ((uint32_t)v & 0xF8u) << (8 * c);
+    }
+    const uint32_t brightRange = (f.range4 + 4u) >> 3;   // :603 floatToByte(range * 0.5)
+    word0 = packed | controlLut[brightRange];
+}
+
+// :684-720 getEtc1SBlockControlByte
+GB_DEV uint32_t etc1_control_word_ref(uint32_t brightRange)
+{
+    const uint32_t cw = (brightRange > 10u) + (brightRange > 21u) + (brightRange > 36u) + (brightRange > 52u) +
+                        (brightRange > 75u) + (brightRange > 90u) + (brightRange > 126u);
+    return (cw * 36u + 3u) << 24;
+}
+
 // The reference's table (goofy_tc.h:1040-1057) steps at 22,44,74,106,152,182,254 and holds
 // (cw<<5 | cw<<2 | 0b11) << 24: both sub-block tables equal, diff = 1, flip = 1.
 GB_DEV uint32_t etc1_control_word(uint32_t range)

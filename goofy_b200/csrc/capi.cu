@@ -49,6 +49,7 @@ int ensure_device_ready(int* deviceOut = nullptr)
     if (dev < 0 || dev >= kMaxDevices) return GOOFY_B200_E_DEVICE;
     std::call_once(g_lutOnce[dev], [dev]() {
         gb::fill_control_lut_kernel<<<1, 256>>>();
+        gb::fill_control_lut_ref_kernel<<<1, 256>>>();
         cudaError_t le = cudaGetLastError();
         if (le == cudaSuccess) le = cudaDeviceSynchronize();
         g_lutStatus[dev] = cuda_rc(le);
@@ -61,6 +62,20 @@ int ensure_device_ready(int* deviceOut = nullptr)
 int check_shape(uint32_t width, uint32_t height, uint32_t stride)
 {
     if (width % 16u != 0u) return GOOFY_B200_E_WIDTH;
+    if (height % 4u != 0u) return GOOFY_B200_E_HEIGHT;
+    if (width == 0u || height == 0u) return GOOFY_B200_OK;
+    if ((uint64_t)stride < (uint64_t)width * 4u) return GOOFY_B200_E_STRIDE;
+    if (stride % 16u != 0u) return GOOFY_B200_E_ALIGN;
+    return GOOFY_B200_OK;
+}
+
+bool is_floatref(int codec) { return codec == GOOFY_B200_DXT1_FLOATREF || codec == GOOFY_B200_ETC1_FLOATREF; }
+bool is_codec(int codec) { return codec == GOOFY_B200_DXT1 || codec == GOOFY_B200_ETC1 || is_floatref(codec); }
+
+// goofyRef:: accepts any width that is a multiple of 4 (Src/goofy_tc_reference.cpp:796-804)
+int check_shape_floatref(uint32_t width, uint32_t height, uint32_t stride)
+{
+    if (width % 4u != 0u) return GOOFY_B200_E_WIDTH;
     if (height % 4u != 0u) return GOOFY_B200_E_HEIGHT;
     if (width == 0u || height == 0u) return GOOFY_B200_OK;
     if ((uint64_t)stride < (uint64_t)width * 4u) return GOOFY_B200_E_STRIDE;
@@ -335,6 +350,59 @@ int encode_uniform(int mode, void* dst, void* dst2, const void* src, uint32_t wi
     }
 }
 
+// Float-reference flavour: one-shot CTAs; batches use grid.z (pitches are free-form).
+int encode_floatref(int codec, void* dst, const void* src, uint32_t width, uint32_t height, uint32_t stride, uint64_t srcPitch,
+                    uint64_t dstPitch, uint32_t nImages, cudaStream_t stream)
+{
+    int rc = check_shape_floatref(width, height, stride);
+    if (rc != GOOFY_B200_OK) return rc;
+    if (width == 0u || height == 0u || nImages == 0u) return GOOFY_B200_OK;
+    rc = check_pointers(src, dst);
+    if (rc != GOOFY_B200_OK) return rc;
+    if (nImages > 1u && ((srcPitch & 15u) != 0u || (dstPitch & 7u) != 0u)) return GOOFY_B200_E_ALIGN;
+    rc = ensure_device_ready();
+    if (rc != GOOFY_B200_OK) return rc;
+    gb::EncodeParams P;
+    P.src = (const uint8_t*)src;
+    P.dst = (uint8_t*)dst;
+    P.dst2 = nullptr;
+    P.bw = width / 4u;
+    P.bh = height / 4u;
+    P.stride = stride;
+    P.srcPitch = srcPitch;
+    P.dstPitch = dstPitch;
+    uint32_t tx = 32u;
+    while (tx < 256u && tx < P.bw) tx <<= 1;
+    const uint32_t ty = 256u / tx;
+    const dim3 block(tx, ty, 1);
+    const uint32_t gx = (P.bw + tx - 1u) / tx, rowsPerLaunch = 65535u * ty;
+    for (uint32_t img0 = 0; img0 < nImages; img0 += 65535u) {
+        const uint32_t nz = nImages - img0 < 65535u ? nImages - img0 : 65535u;
+        for (uint32_t by0 = 0; by0 < P.bh; by0 += rowsPerLaunch) {
+            const uint32_t rows = P.bh - by0 < rowsPerLaunch ? P.bh - by0 : rowsPerLaunch;
+            gb::EncodeParams Q = P;
+            Q.by0 = by0;
+            Q.src += (uint64_t)img0 * srcPitch;
+            Q.dst += (uint64_t)img0 * dstPitch;
+            const dim3 grid(gx, (rows + ty - 1u) / ty, nz);
+            if (codec == GOOFY_B200_DXT1_FLOATREF) gb::encode_floatref_kernel<gb::kDxt1><<<grid, block, 0, stream>>>(Q);
+            else gb::encode_floatref_kernel<gb::kEtc1><<<grid, block, 0, stream>>>(Q);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            GB_CUDA(cudaGetLastError());
+        }
+    }
+    return GOOFY_B200_OK;
+}
+
+// Device-resident dispatch by codec selector (SSE2-exact or float-reference-exact flavour).
+int encode_any(int codec, void* dst, const void* src, uint32_t width, uint32_t height, uint32_t stride, uint64_t srcPitch,
+               uint64_t dstPitch, uint32_t nImages, cudaStream_t stream)
+{
+    if (!is_codec(codec)) return GOOFY_B200_E_CODEC;
+    if (is_floatref(codec)) return encode_floatref(codec, dst, src, width, height, stride, srcPitch, dstPitch, nImages, stream);
+    return encode_uniform(codec, dst, nullptr, src, width, height, stride, srcPitch, dstPitch, nImages, stream);
+}
+
 // ---------------------------------------------------------------- host-pointer pipeline
 // The image is cut into strips of whole block rows; strip i runs H2D -> kernel -> D2H on
 // stream i % kSlots so the copies of neighbouring strips overlap each other and the kernels.
@@ -396,8 +464,8 @@ thread_local HostPipe t_pipe;
 
 int encode_host(int codec, void* result, const void* input, uint32_t width, uint32_t height, uint32_t stride)
 {
-    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
-    int rc = check_shape(width, height, stride);
+    if (!is_codec(codec)) return GOOFY_B200_E_CODEC;
+    int rc = is_floatref(codec) ? check_shape_floatref(width, height, stride) : check_shape(width, height, stride);
     if (rc != GOOFY_B200_OK) return rc;
     if (width == 0u || height == 0u) return GOOFY_B200_OK;
     if (!result || !input) return GOOFY_B200_E_NULL;
@@ -422,8 +490,7 @@ int encode_host(int codec, void* result, const void* input, uint32_t width, uint
         // stream order protects the slot's scratch: its previous strip finished D2H on the same stream
         GB_CUDA(cudaMemcpy2DAsync(t_pipe.dIn[slot], rowBytes, (const uint8_t*)input + (size_t)r0 * 4u * stride, stride,
                                   rowBytes, (size_t)rows * 4u, cudaMemcpyHostToDevice, s));
-        rc = encode_uniform(codec, t_pipe.dOut[slot], nullptr, t_pipe.dIn[slot], width, rows * 4u, (uint32_t)rowBytes, 0, 0,
-                            1, s);
+        rc = encode_any(codec, t_pipe.dOut[slot], t_pipe.dIn[slot], width, rows * 4u, (uint32_t)rowBytes, 0, 0, 1, s);
         if (rc != GOOFY_B200_OK) return rc;
         GB_CUDA(cudaMemcpyAsync((uint8_t*)result + (size_t)r0 * outRowBytes, t_pipe.dOut[slot], (size_t)rows * outRowBytes,
                                 cudaMemcpyDeviceToHost, s));
@@ -654,17 +721,27 @@ int goofy_b200_encode_host(int codec, void* result, const void* input, uint32_t 
 int goofy_b200_encode_device(int codec, void* d_result, const void* d_input, uint32_t width, uint32_t height,
                              uint32_t stride, void* stream)
 {
-    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
-    return encode_uniform(codec, d_result, nullptr, d_input, width, height, stride, 0, 0, 1, (cudaStream_t)stream);
+    return encode_any(codec, d_result, d_input, width, height, stride, 0, 0, 1, (cudaStream_t)stream);
+}
+
+int goofy_b200_compress_dxt1_floatref(unsigned char* result, const unsigned char* input, unsigned int width,
+                                      unsigned int height, unsigned int stride)
+{
+    return encode_host(GOOFY_B200_DXT1_FLOATREF, result, input, width, height, stride);
+}
+
+int goofy_b200_compress_etc1_floatref(unsigned char* result, const unsigned char* input, unsigned int width,
+                                      unsigned int height, unsigned int stride)
+{
+    return encode_host(GOOFY_B200_ETC1_FLOATREF, result, input, width, height, stride);
 }
 
 int goofy_b200_encode_batch_uniform_device(int codec, void* d_result, const void* d_input, uint32_t width, uint32_t height,
                                            uint32_t stride, uint64_t input_image_pitch, uint64_t result_image_pitch,
                                            uint32_t n_images, void* stream)
 {
-    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
-    return encode_uniform(codec, d_result, nullptr, d_input, width, height, stride, input_image_pitch, result_image_pitch,
-                          n_images, (cudaStream_t)stream);
+    return encode_any(codec, d_result, d_input, width, height, stride, input_image_pitch, result_image_pitch, n_images,
+                      (cudaStream_t)stream);
 }
 
 int goofy_b200_encode_dual_device(void* d_result_dxt1, void* d_result_etc1, const void* d_input, uint32_t width,

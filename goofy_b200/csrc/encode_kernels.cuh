@@ -210,6 +210,39 @@ __global__ void __launch_bounds__(256, 5) encode_rows_prefetch_kernel(const Enco
     }
 }
 
+// Float-reference flavour (goofyRef::, block_codec.cuh "float-reference flavour"): one-shot CTAs,
+// any width that is a multiple of 4.  `lutRef` is the goofyRef control table by brightRange.
+__device__ uint32_t g_etc1ControlLutRef[256];
+
+__global__ void fill_control_lut_ref_kernel() { g_etc1ControlLutRef[threadIdx.x] = etc1_control_word_ref(threadIdx.x); }
+
+template <int CODEC>
+__global__ void __launch_bounds__(256) encode_floatref_kernel(const EncodeParams P)
+{
+    __shared__ uint32_t lut[CODEC == kDxt1 ? 1 : 256];
+    if (CODEC != kDxt1) {
+        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
+        lut[t] = g_etc1ControlLutRef[t];
+        __syncthreads();
+    }
+    const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t by = P.by0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (bx >= P.bw || by >= P.bh) return;
+    const uint8_t* s = P.src + (uint64_t)blockIdx.z * P.srcPitch + (uint64_t)by * 4u * P.stride + (uint64_t)bx * 16u;
+    const uint4 r0 = load_row(s);
+    const uint4 r1 = load_row(s + P.stride);
+    const uint4 r2 = load_row(s + 2ull * P.stride);
+    const uint4 r3 = load_row(s + 3ull * P.stride);
+    const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
+                            r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+    // minimum brightness range: 8 for DXT1 (:667), 16 for ETC1S (:766), times 4
+    const RefFront f = analyse_ref(p, CODEC == kDxt1 ? 32u : 64u);
+    uint32_t w0, w1;
+    if (CODEC == kDxt1) encode_dxt1_ref(p, f, w0, w1);
+    else encode_etc1_ref(p, f, lut, w0, w1);
+    store_block(P.dst + (uint64_t)blockIdx.z * P.dstPitch + ((uint64_t)by * P.bw + bx) * 8u, w0, w1);
+}
+
 // ------------------------------------------------------------------ ragged batches
 // Images of different shapes in one launch.  The host sorts nothing: it uploads the
 // descriptors plus an exclusive prefix sum of per-image CTA counts; each CTA finds its

@@ -38,6 +38,12 @@ extern "C" {
 /* codec selectors */
 #define GOOFY_B200_DXT1 0
 #define GOOFY_B200_ETC1 1
+/* Second flavour: bit-exact with the reference's float "idea" encoder goofyRef::compressDXT1/ETC1
+ * (Src/goofy_tc_reference.cpp:794-850) instead of with the SSE2 path.  The two flavours differ
+ * by design (rounding, tie-break, minimum range, table thresholds).  Accepted by the host,
+ * device and uniform-batch entry points; width only needs to be a multiple of 4 (:796). */
+#define GOOFY_B200_DXT1_FLOATREF 16
+#define GOOFY_B200_ETC1_FLOATREF 17
 
 /* return codes: 0, -1, -2 are the reference's; the rest are new and never collide with them */
 #define GOOFY_B200_OK 0
@@ -86,6 +92,11 @@ int goofy_b200_compress_dxt1(unsigned char* result, const unsigned char* input, 
                              unsigned int height, unsigned int stride);
 int goofy_b200_compress_etc1(unsigned char* result, const unsigned char* input, unsigned int width,
                              unsigned int height, unsigned int stride);
+/* goofyRef::compressDXT1 / compressETC1 (Src/goofy_tc_reference.h:7-8) -- the float-reference flavour. */
+int goofy_b200_compress_dxt1_floatref(unsigned char* result, const unsigned char* input, unsigned int width,
+                                      unsigned int height, unsigned int stride);
+int goofy_b200_compress_etc1_floatref(unsigned char* result, const unsigned char* input, unsigned int width,
+                                      unsigned int height, unsigned int stride);
 /* Same, codec chosen at run time.  Host buffers may be pageable or pinned; pinned buffers
  * (cudaHostAlloc / cudaHostRegister) are copied without a staging hop.  Uses the calling
  * thread's current device and synchronises before returning. */

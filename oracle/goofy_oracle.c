@@ -184,6 +184,116 @@ int goofy_oracle_compress_etc1(uint8_t* result, const uint8_t* input, unsigned w
     return compress_image(result, input, width, height, stride, goofy_oracle_block_etc1);
 }
 
+/* ------------------------------------------------------------------ float-reference flavour
+ * Restates goofyCompressBlock and its two packers with the same float expressions
+ * (Src/goofy_tc_reference.cpp:514-623).  Every intermediate is a multiple of 1/64 below 2^15,
+ * so float evaluation is exact and compiler contraction cannot change the result. */
+typedef struct {
+    unsigned mn[3], mx[3], base[3];
+    unsigned bright_range;
+    int index[16];
+} floatref_block;
+
+static unsigned float_to_byte(float v) /* :350-361 */
+{
+    v = v + 0.5f;
+    if (v < 0.0f) v = 0.0f;
+    if (v > 255.0f) v = 255.0f;
+    return (unsigned)(uint8_t)v;
+}
+
+static float brightness_f(float r, float g, float b) { return r * 0.25f + g * 0.5f + b * 0.25f; } /* :246-250 */
+
+static void floatref_analyse(const uint8_t* px, size_t stride, float min_range, floatref_block* o)
+{
+    float mn[3] = {99999.0f, 99999.0f, 99999.0f}, mx[3] = {-99999.0f, -99999.0f, -99999.0f}, avg[3] = {0, 0, 0};
+    for (int y = 0; y < 4; ++y)
+        for (int x = 0; x < 4; ++x)
+            for (int c = 0; c < 3; ++c) {
+                float v = (float)px[(size_t)y * stride + 4u * (unsigned)x + (unsigned)c];
+                if (v < mn[c]) mn[c] = v;
+                if (v > mx[c]) mx[c] = v;
+                avg[c] += v;
+            }
+    for (int c = 0; c < 3; ++c) avg[c] /= 16.0f;
+    float maxY = brightness_f(mx[0], mx[1], mx[2]), minY = brightness_f(mn[0], mn[1], mn[2]);
+    float range = maxY - minY;
+    if (range < min_range) range = min_range;                       /* :549 */
+    float mid = (maxY + minY) * 0.5f;                               /* :551 */
+    float q = range * 0.375f;                                       /* :554 */
+    for (int y = 0; y < 4; ++y)
+        for (int x = 0; x < 4; ++x) {
+            const uint8_t* p = px + (size_t)y * stride + 4u * (unsigned)x;
+            float diff = brightness_f((float)p[0], (float)p[1], (float)p[2]) - mid;
+            float ad = diff < 0.0f ? -diff : diff;
+            o->index[4 * y + x] = diff > 0.0f ? (diff < q ? 2 : 0) : (ad < q ? 3 : 1);   /* :579-589 */
+        }
+    for (int c = 0; c < 3; ++c) {
+        o->mn[c] = float_to_byte(mn[c]);
+        o->mx[c] = float_to_byte(mx[c]);
+    }
+    o->bright_range = float_to_byte(range * 0.5f);                  /* :603 */
+    float avgY = brightness_f(avg[0], avg[1], avg[2]);
+    float diffY = mid - avgY;                                       /* :606-608 */
+    for (int c = 0; c < 3; ++c) o->base[c] = float_to_byte(avg[c] + diffY);
+}
+
+static void floatref_block_dxt1(const uint8_t* px, size_t stride, uint8_t* out)
+{
+    floatref_block b;
+    floatref_analyse(px, stride, 8.0f, &b);                         /* :667 */
+    uint32_t c0 = ((b.mx[0] >> 3) << 11) | ((b.mx[1] >> 3) << 6) | (b.mx[2] >> 3) | 0x20u;   /* :634-646, :670 */
+    uint32_t c1 = ((b.mn[0] >> 3) << 11) | ((b.mn[1] >> 3) << 6) | (b.mn[2] >> 3);
+    uint32_t idx = 0;
+    for (int n = 0; n < 16; ++n) idx |= (uint32_t)(b.index[n] & 3) << (2 * n);              /* :648-657 */
+    store_le32(out, c0 | (c1 << 16));
+    store_le32(out + 4, idx);
+}
+
+static void floatref_block_etc1(const uint8_t* px, size_t stride, uint8_t* out)
+{
+    static const unsigned table[7] = {10u, 21u, 36u, 52u, 75u, 90u, 126u};                  /* :688 */
+    floatref_block b;
+    floatref_analyse(px, stride, 16.0f, &b);                        /* :766 */
+    unsigned cw = 0;
+    while (cw < 7u && b.bright_range > table[cw]) ++cw;
+    uint32_t word0 = (b.base[0] & 0xF8u) | ((b.base[1] & 0xF8u) << 8) | ((b.base[2] & 0xF8u) << 16) |   /* :625-632 */
+                     (((cw << 5) | (cw << 2) | 3u) << 24);
+    uint32_t v = 0;
+    for (int n = 0; n < 16; ++n) {                                  /* :722-756 */
+        int x = n & 3, y = n >> 2;
+        unsigned bit = (unsigned)(((x ^ 2) << 2) + y);
+        unsigned far_ = (b.index[n] == 0 || b.index[n] == 1), neg = (b.index[n] == 1 || b.index[n] == 3);
+        v |= (uint32_t)neg << bit;
+        v |= (uint32_t)far_ << (bit + 16);
+    }
+    store_le32(out, word0);
+    store_le32(out + 4, v);
+}
+
+static int floatref_compress(uint8_t* result, const uint8_t* input, unsigned width, unsigned height, unsigned stride,
+                             void (*block_fn)(const uint8_t*, size_t, uint8_t*))
+{
+    if (width % 4u != 0u) return -1;                                /* :796-804 */
+    if (height % 4u != 0u) return -2;
+    for (unsigned by = 0; by < height / 4u; ++by)
+        for (unsigned bx = 0; bx < width / 4u; ++bx) {
+            block_fn(input + (size_t)by * 4u * stride + (size_t)bx * 16u, stride, result);
+            result += 8;
+        }
+    return 0;
+}
+
+int goofy_oracle_floatref_compress_dxt1(uint8_t* result, const uint8_t* input, unsigned width, unsigned height, unsigned stride)
+{
+    return floatref_compress(result, input, width, height, stride, floatref_block_dxt1);
+}
+
+int goofy_oracle_floatref_compress_etc1(uint8_t* result, const uint8_t* input, unsigned width, unsigned height, unsigned stride)
+{
+    return floatref_compress(result, input, width, height, stride, floatref_block_etc1);
+}
+
 /* ------------------------------------------------------------------ decoders */
 
 static inline uint32_t load_le32(const uint8_t* p)

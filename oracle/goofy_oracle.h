@@ -44,6 +44,17 @@ int goofy_oracle_compress_dxt1(uint8_t* result, const uint8_t* input,
 int goofy_oracle_compress_etc1(uint8_t* result, const uint8_t* input,
                                unsigned width, unsigned height, unsigned stride);
 
+/* Second flavour: the reference's float "idea" encoder goofyRef::compressDXT1/ETC1
+ * (Src/goofy_tc_reference.cpp:514-623, :634-670, :684-792).  It is NOT bit-equal to the SSE2
+ * path (different rounding, tie-break, minimum range and table thresholds); it is restated
+ * here with the same float expressions.  Shapes: width%4 (-1), height%4 (-2) like :794-850.
+ * Block rows advance by `stride` (the reference advances by width*16 bytes, which is the same
+ * thing for the tight stride its harness always uses). */
+int goofy_oracle_floatref_compress_dxt1(uint8_t* result, const uint8_t* input,
+                                        unsigned width, unsigned height, unsigned stride);
+int goofy_oracle_floatref_compress_etc1(uint8_t* result, const uint8_t* input,
+                                        unsigned width, unsigned height, unsigned stride);
+
 /* Decode whole images of 8-byte blocks (row-major block order) to tight RGBA8.
  * Alpha is written as 255 (BC1 3-colour "transparent" index writes 0,0,0,0
  * like Src/decoder.cpp:836-851). */

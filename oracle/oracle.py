@@ -67,7 +67,8 @@ class Oracle(_Encoder):
         build()
         lib = C.CDLL(str(ORACLE_DIR / "liboracle.so"))
         sig = [_u8p, _u8p, C.c_uint, C.c_uint, C.c_uint]
-        for name in ("goofy_oracle_compress_dxt1", "goofy_oracle_compress_etc1"):
+        for name in ("goofy_oracle_compress_dxt1", "goofy_oracle_compress_etc1",
+                     "goofy_oracle_floatref_compress_dxt1", "goofy_oracle_floatref_compress_etc1"):
             getattr(lib, name).argtypes = sig
             getattr(lib, name).restype = C.c_int
         for name in ("goofy_oracle_decode_dxt1", "goofy_oracle_decode_etc1"):
@@ -78,6 +79,16 @@ class Oracle(_Encoder):
         self.lib = lib
         self._fn = {DXT1: lib.goofy_oracle_compress_dxt1, ETC1: lib.goofy_oracle_compress_etc1}
         self._dec = {DXT1: lib.goofy_oracle_decode_dxt1, ETC1: lib.goofy_oracle_decode_etc1}
+        self._floatref = {DXT1: lib.goofy_oracle_floatref_compress_dxt1, ETC1: lib.goofy_oracle_floatref_compress_etc1}
+
+    def compress_float_reference(self, codec: int, img: np.ndarray, width: int, height: int, stride: int | None = None):
+        """Restatement of goofyRef:: (Src/goofy_tc_reference.cpp), the reference's float flavour."""
+        stride = width * 4 if stride is None else stride
+        img = np.ascontiguousarray(img).reshape(-1)
+        _check_image(img, width, height, stride)
+        out = np.zeros(width * height // 2, dtype=np.uint8)
+        rc = self._floatref[codec](_ptr(out), _ptr(img), width, height, stride)
+        return rc, out
 
     def decode(self, codec: int, blocks: np.ndarray, width: int, height: int) -> np.ndarray:
         blocks = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)

@@ -12,18 +12,26 @@
 extern "C" int kernel_math_compress(int codec, unsigned char* result, const unsigned char* input, unsigned width,
                                     unsigned height, unsigned stride)
 {
-    if (width % 16) return -1;
+    const bool floatRef = (codec & 16) != 0;   // GOOFY_B200_FLOATREF flavours (codec 16 / 17); goofyRef accepts width % 4
+    codec &= 15;
+    if (width % (floatRef ? 4 : 16)) return -1;
     if (height % 4) return -2;
     uint32_t lut[256];
-    for (uint32_t r = 0; r < 256; ++r) lut[r] = gb::etc1_control_word(r);
+    for (uint32_t r = 0; r < 256; ++r) lut[r] = floatRef ? gb::etc1_control_word_ref(r) : gb::etc1_control_word(r);
     for (unsigned by = 0; by < height / 4; ++by)
         for (unsigned bx = 0; bx < width / 4; ++bx) {
             uint32_t p[16];
             for (int y = 0; y < 4; ++y) std::memcpy(&p[4 * y], input + (size_t)(4 * by + y) * stride + (size_t)bx * 16, 16);
             uint32_t w0, w1;
-            const gb::BlockFront f = gb::analyse(p);
-            if (codec == 0) gb::encode_dxt1(p, f, w0, w1);
-            else gb::encode_etc1(p, f, lut, w0, w1);
+            if (floatRef) {
+                const gb::RefFront f = gb::analyse_ref(p, codec == 0 ? 32u : 64u);
+                if (codec == 0) gb::encode_dxt1_ref(p, f, w0, w1);
+                else gb::encode_etc1_ref(p, f, lut, w0, w1);
+            } else {
+                const gb::BlockFront f = gb::analyse(p);
+                if (codec == 0) gb::encode_dxt1(p, f, w0, w1);
+                else gb::encode_etc1(p, f, lut, w0, w1);
+            }
             std::memcpy(result, &w0, 4);
             std::memcpy(result + 4, &w1, 4);
             result += 8;

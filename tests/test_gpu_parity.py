@@ -358,3 +358,42 @@ def test_gpu_psnr_of_test_images_matches_reference_numbers(oracle):
             torch.cuda.synchronize()
             vals.append(gb.psnr_rgb768(d_sse.cpu().tolist(), w * h))
         assert abs(float(np.mean(vals)) - want) < 0.01, (codec, np.mean(vals))
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_floatref_flavour_bit_exact_vs_goofyref(codec, oracle):
+    """GOOFY_B200_*_FLOATREF: bit-exact with goofyRef:: (Src/goofy_tc_reference.cpp) -- checked against our float
+    restatement everywhere and against the unmodified reference where oracle/_ref is present."""
+    from oracle.oracle import Reference
+    ref = Reference() if Reference.available() else None
+    fcodec = {DXT1: gb.DXT1_FLOATREF, ETC1: gb.ETC1_FLOATREF}[codec]
+    host_fn = {DXT1: gb.goofyRef.compressDXT1, ETC1: gb.goofyRef.compressETC1}[codec]
+    cases = [synth_family(f, 512, 256, seed=3 + f) for f in range(4)]
+    cases.append(splitmix_rgba(20 * 12, seed=8).reshape(12, 20, 4))     # width % 4 only
+    cases.append(splitmix_rgba(1036 * 8, seed=9).reshape(8, 1036, 4))
+    for n in image_names():
+        cases.append(load_test_image(n))
+    for img in cases:
+        h, w = img.shape[:2]
+        want = oracle.compress_float_reference(codec, img, w, h)[1]
+        if ref is not None:
+            assert np.array_equal(want, ref.compress_float_reference(codec, aligned_copy(img), w, h)[1])
+        rc, got = gpu_device(fcodec, img, w, h)
+        assert rc == 0 and np.array_equal(got, want), (w, h)
+        out = np.zeros(w * h // 2, dtype=np.uint8)
+        assert host_fn(out, aligned_copy(img), w, h, w * 4) == 0 and np.array_equal(out, want)
+    # and it is a different result from the SSE2-exact flavour, as surveyed
+    img = cases[1]
+    assert not np.array_equal(gpu_device(fcodec, img, 512, 256)[1], gpu_device(codec, img, 512, 256)[1])
+    buf = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    src = torch.zeros(64 * 64 * 4, dtype=torch.uint8, device="cuda")
+    assert gb.encode_device(fcodec, buf, src, 18, 8, 80) == -1
+    assert gb.encode_device(fcodec, buf, src, 20, 6, 80) == -2
+    # uniform batch with free-form pitches
+    n, w, h = 3, 64, 16
+    imgs = np.stack([synth_family(i, w, h, seed=70 + i) for i in range(n)])
+    d_dst = torch.zeros((n, w * h // 2 + 8), dtype=torch.uint8, device="cuda")
+    assert gb.encode_batch_uniform_device(fcodec, d_dst, dev(imgs), w, h, w * 4, w * h * 4, w * h // 2 + 8, n) == 0
+    torch.cuda.synchronize()
+    for i in range(n):
+        assert np.array_equal(d_dst[i].cpu().numpy()[: w * h // 2], oracle.compress_float_reference(codec, imgs[i], w, h)[1])

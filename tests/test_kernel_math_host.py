@@ -46,3 +46,24 @@ def test_kernel_math_return_codes(codec, kernel_math):
     img = splitmix_rgba(64 * 64, seed=1)
     assert kernel_math(codec, img, 24, 32)[0] == -1
     assert kernel_math(codec, img, 32, 6)[0] == -2
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_floatref_kernel_math(codec, kernel_math, oracle):
+    """Integer re-derivation of the float reference (block_codec.cuh, float-reference flavour) vs the float oracle."""
+    rng = np.random.default_rng(11)
+    cases = [synth_family(f, 256, 256, seed=31 + f) for f in range(4)]
+    for spread in (0, 1, 2, 7, 8, 9, 15, 16, 17, 20, 21, 22, 41, 42, 43, 72, 104, 150, 180, 252, 255):
+        base = rng.integers(0, 256 - spread, size=(32, 32, 1, 1, 3))
+        blk = base + rng.integers(0, spread + 1, size=(32, 32, 4, 4, 3))
+        img = np.zeros((128, 128, 4), dtype=np.uint8)
+        img[..., :3] = blk.transpose(0, 2, 1, 3, 4).reshape(128, 128, 3)
+        cases.append(img)
+    fx = np.load("tests/golden/fixtures.npz")
+    cases += [fx[k] for k in fx.files if k.endswith("_rgba")]
+    for img in cases:
+        h, w = img.shape[:2]
+        rc, got = kernel_math(16 + codec, img, w, h)
+        assert rc == 0 and np.array_equal(got, oracle.compress_float_reference(codec, img, w, h)[1])
+    assert kernel_math(16 + codec, splitmix_rgba(20 * 8, seed=1), 20, 8)[0] == 0
+    assert kernel_math(16 + codec, splitmix_rgba(64 * 64, seed=1), 18, 8)[0] == -1

@@ -173,3 +173,30 @@ def test_float_reference_differs_as_surveyed(reference, oracle):
     b = reference.compress_float_reference(DXT1, aligned_copy(img), w, h)[1].reshape(-1, 8)
     differing = int((a != b).any(axis=1).sum())
     assert differing == 17463  # kodim01 DXT1 17463/24576
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_floatref_oracle_vs_unmodified_goofyref(codec, oracle, reference):
+    """The second flavour: our restatement of goofyRef:: (Src/goofy_tc_reference.cpp) against the real one."""
+    cases = [synth_family(f, 256, 128, seed=21) for f in range(4)]
+    rng = np.random.default_rng(5)
+    for spread in (0, 1, 3, 7, 8, 15, 16, 17, 31, 33, 60, 120, 255):
+        base = rng.integers(0, 256 - spread, size=(32, 64, 1, 1, 3))
+        blk = base + rng.integers(0, spread + 1, size=(32, 64, 4, 4, 3))
+        img = np.zeros((128, 256, 4), dtype=np.uint8)
+        img[..., :3] = blk.transpose(0, 2, 1, 3, 4).reshape(128, 256, 3)
+        cases.append(img)
+    for n in image_names()[:12]:
+        cases.append(load_test_image(n))
+    for img in cases:
+        h, w = img.shape[:2]
+        a = oracle.compress_float_reference(codec, img, w, h)
+        b = reference.compress_float_reference(codec, aligned_copy(img), w, h)
+        assert a[0] == b[0] == 0 and np.array_equal(a[1], b[1])
+    # goofyRef accepts any width that is a multiple of 4 (:796)
+    img = splitmix_rgba(20 * 8, seed=4)
+    a = oracle.compress_float_reference(codec, img, 20, 8)
+    b = reference.compress_float_reference(codec, aligned_copy(img), 20, 8)
+    assert a[0] == b[0] == 0 and np.array_equal(a[1], b[1])
+    assert oracle.compress_float_reference(codec, img, 18, 8)[0] == -1
+    assert oracle.compress_float_reference(codec, img, 20, 6)[0] == -2

@@ -34,6 +34,10 @@
 #define P_IMADHI(d, a, b) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(d) : "r"(a), "r"(b));
 #define P_IMADWIDE(d, a, b) asm volatile("{.reg .b64 t, u; mov.b64 u, {%0, %1}; mad.wide.u32 t, %0, %2, u; mov.b64 {%0, %1}, t;}" : "+r"(d), "+r"(a) : "r"(b));
 #define P_LEA(d, a, b) asm volatile("{.reg .b32 t; shl.b32 t, %0, 3; add.u32 %0, t, %1;}" : "+r"(d) : "r"(a));
+#define P_WIDE(d, a, b) asm volatile("{.reg .b64 t, u; mov.b64 u, {%0, %1}; mad.wide.u32 t, %2, %2, u; mov.b64 {%0, %1}, t;}" : "+r"(d), "+r"(a) : "r"(b));
+#define P_HMNMX2(d, a, b) asm volatile("min.f16x2 %0, %0, %1;" : "+r"(d) : "r"(a));
+#define P_FMNMX(d, a, b) asm volatile("min.f32 %0, %0, %1;" : "+r"(d) : "r"(a));
+#define P_HFMA2(d, a, b) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(d) : "r"(a), "r"(b));
 #define P_ISETP_SEL(d, a, b) asm volatile("{.reg .pred p; setp.lt.u32 p, %0, %1; selp.b32 %0, %1, %2, p;}" : "+r"(d) : "r"(a), "r"(b));
 
 #define DEFINE_KERNEL(NAME, BODY)                                                                   \
@@ -71,6 +75,14 @@ DEFINE_KERNEL(k_ffma, ROUND(P_FFMA))
 DEFINE_KERNEL(k_absd4, ROUND(P_ABSD4))
 DEFINE_KERNEL(k_popc, ROUND(P_POPC))
 DEFINE_KERNEL(k_setp_sel, ROUND(P_ISETP_SEL))
+DEFINE_KERNEL(k_wide, ROUND(P_WIDE))
+DEFINE_KERNEL(k_lop3_wide, ROUND2(P_LOP3, P_WIDE))
+DEFINE_KERNEL(k_hmnmx2, ROUND(P_HMNMX2))
+DEFINE_KERNEL(k_fmnmx, ROUND(P_FMNMX))
+DEFINE_KERNEL(k_hfma2, ROUND(P_HFMA2))
+DEFINE_KERNEL(k_lop3_hmnmx2, ROUND2(P_LOP3, P_HMNMX2))
+DEFINE_KERNEL(k_imad_hmnmx2, ROUND2(P_IMAD, P_HMNMX2))
+DEFINE_KERNEL(k_lop3_fmnmx, ROUND2(P_LOP3, P_FMNMX))
 DEFINE_KERNEL(k_imadhi, ROUND(P_IMADHI))
 DEFINE_KERNEL(k_lea, ROUND(P_LEA))
 DEFINE_KERNEL(k_lop3_imadhi, ROUND2(P_LOP3, P_IMADHI))
@@ -124,6 +136,8 @@ int main()
         {"idp4a", k_idp}, {"vimnmx.u16x2", k_mnmx2}, {"vimnmx3.u16x2", k_mnmx3}, {"viaddmnmx", k_addmnmx},
         {"viadd.16x2", k_vadd2}, {"(x>>1)+a", k_leahi}, {"fadd", k_fadd}, {"ffma", k_ffma}, {"vabsdiff4", k_absd4},
         {"popc+xor", k_popc}, {"setp+selp", k_setp_sel},
+        {"imad.wide", k_wide}, {"lop3+imad.wide", k_lop3_wide}, {"hmnmx2", k_hmnmx2}, {"fmnmx", k_fmnmx}, {"hfma2", k_hfma2},
+        {"lop3+hmnmx2", k_lop3_hmnmx2}, {"imad+hmnmx2", k_imad_hmnmx2}, {"lop3+fmnmx", k_lop3_fmnmx},
         {"imad.hi", k_imadhi}, {"(x<<3)+a", k_lea}, {"lop3+imad.hi", k_lop3_imadhi}, {"lop3+(x<<3)+a", k_lop3_lea},
         {"lop3+imad", k_lop3_imad}, {"lop3+idp", k_lop3_idp}, {"imad+idp", k_imad_idp},
         {"lop3+mnmx2", k_lop3_mnmx2}, {"lop3+mnmx3", k_lop3_mnmx3}, {"imad+mnmx2", k_imad_mnmx2}, {"imad+mnmx3", k_imad_mnmx3},
