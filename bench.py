@@ -34,7 +34,7 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--codec", choices=["dxt1", "etc1"], default="dxt1")
@@ -310,6 +310,13 @@ def run_b200_arm(args):
     bytes_per_launch = px_per_step * BYTES_PER_PIXEL / launches_per_step
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = hbm_peak()
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu capture
+    try:
+        tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        if size == 8192 and batch == 4:
+            traffic = tj["dram_bytes_per_launch"].get(args.codec)
+    except Exception:
+        traffic = None
 
     # same batch, one launch per texture (what a caller encoding single 8192^2 textures sees)
     side_steps = max(min(args.steps // 2, 100), 3)
@@ -389,7 +396,7 @@ def run_b200_arm(args):
                        "load_path": args.load_path,
                        "sharding": "one batch per rank, no collectives" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "kernel": ("encode_direct_kernel" if codec == gb.DXT1 and args.load_path in ("auto", "oneshot")
                                     else "encode_tma_kernel" if args.load_path == "tma" else "encode_rows_kernel") + f"<{args.codec}>",
                          "bytes_per_launch": bytes_per_launch, "launch_ms": launch_ms,

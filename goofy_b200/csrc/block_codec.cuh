@@ -22,7 +22,8 @@
 
 namespace gb {
 
-constexpr uint32_t kLuma = 0x00010201u;  // dp4a weights for bytes (R,G,B,A): R + 2G + B
+constexpr uint32_t kLuma = 0x00010201u;   // dp4a weights for bytes (R,G,B,A): R + 2G + B
+constexpr uint32_t kLuma2 = 0x00020402u;  // twice that
 
 // min / max of 16 words, two u16 lanes each, in 8 three-input ops
 template <bool kMax>
@@ -50,6 +51,10 @@ struct BlockFront {
     uint32_t mid;         // avg(minY, maxY)                      goofy_tc.h:1179
     uint32_t laneBias;    // dp4a accumulator that makes lane = (R+2G+B+3) - 4*mid + 0x4000
     uint32_t kLo, kHi;    // packed add constants: bit15 of (lane + kLo) <=> e >= 4 - 4qt, of (lane + kHi) <=> e >= 4qt
+    // single-pixel form used by the ETC1s planes (everything on the multiply pipe):
+    uint32_t cE;          // dp4a(pixel, kLuma,  cE) = e            -> bit31 <=> !Gez
+    uint32_t cT;          // dp4a(pixel, kLuma2, cT) = t = 2e - 3
+    uint32_t cU;          // t*t + cU                                -> bit31 <=> !Lqt   (Lqt <=> |2e-3| <= 8qt-5)
 };
 
 GB_DEV BlockFront analyse(const uint32_t (&p)[16])
@@ -78,6 +83,10 @@ GB_DEV BlockFront analyse(const uint32_t (&p)[16])
     f.laneBias = 0x4003u - (f.mid << 2);
     f.kLo = (0x3FFCu + q4) * 0x10001u;
     f.kHi = (0x4000u - q4) * 0x10001u;
+    f.cE = 3u - (f.mid << 2);
+    f.cT = 2u * f.cE - 3u;
+    const uint32_t a = 2u * q4 - 5u;   // 8qt - 5, 19..763
+    f.cU = 0x7FFFFFFFu - a * a;        // 2^31 - ((8qt-5)^2 + 1)
     return f;
 }
 
@@ -130,22 +139,45 @@ GB_DEV uint32_t floor_avg4_of_complements(uint32_t a, uint32_t b) { return nor(a
 // Output (goofy_tc.h:1358-1493): word0 = R5<<3 | G5<<11 | B5<<19 | control<<24;
 // word1 = ~(GezPlane | LqtPlane << 16), pixel (x,y) at plane bit ((x^2)<<2)+y.
 // `controlLut[range]` = control byte << 24 (the reference's table, goofy_tc.h:1040-1057).
+// kPixelPlanes selects how the two selector planes are gathered (same result):
+//   true   one pixel at a time on the multiply pipe (3 IDP/IMAD + 2 funnel shifts per pixel) -- relieves the
+//          integer ALU pipe, which is what bounds the ETC1s-only kernel (+1.6 % measured);
+//   false  two pixels per register as biased u16 lanes (the DXT1 scheme) -- fewer instructions in total, which
+//          is what the dual-output kernel needs (6478 vs 6068 GB/s measured).
+template <bool kPixelPlanes = true>
 GB_DEV void encode_etc1(const uint32_t (&p)[16], const BlockFront& f, const uint32_t* controlLut, uint32_t& word0,
                         uint32_t& word1)
 {
-    // Plane bit order is column major starting at column 2: low lane walks columns 2,3
-    // (plane bits 0..7), high lane columns 0,1 (plane bits 8..15).
-    uint32_t accNeg = 0, accFar = 0;
+    // The two selector planes, one pixel at a time, entirely on the multiply pipe plus one funnel
+    // shift per flag: e = S - 4*mid has !Gez in its sign bit; with t = 2e - 3, Lqt <=> t^2 <= (8qt-5)^2,
+    // so t*t + (2^31 - (8qt-5)^2 - 1) has !Lqt in bit 31.  Pixels are pushed from plane bit 15 down
+    // to 0 (plane bit of pixel (x,y) is ((x^2)<<2)+y), so the accumulators ARE the planes.
+    if (kPixelPlanes) {
+        uint32_t accNeg = 0, accFar = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int y = k & 3, x = k >> 2;
-        const uint32_t e = lanes_of(p[4 * y + 2 + x], p[4 * y + x], f.laneBias);
-        const uint32_t x2 = lqt_lanes(e, f);
-        accNeg = bitsel(~e, accNeg >> 1, 0x40004000u);   // !Gez
-        accFar = bitsel(~x2, accFar >> 1, 0x80008000u);  // !Lqt
+        for (int b = 15; b >= 0; --b) {
+            const int x = (b >> 2) ^ 2, y = b & 3;
+            const uint32_t px = p[4 * y + x];
+            const uint32_t e = dp4a(px, kLuma, f.cE);
+            const uint32_t t = dp4a(px, kLuma2, f.cT);
+            accNeg = push_top_bit(accNeg, e);
+            accFar = push_top_bit(accFar, t * t + f.cU);
+        }
+        word1 = accNeg | (accFar << 16);
+    } else {
+        // low lane walks columns 2,3 (plane bits 0..7), high lane columns 0,1 (plane bits 8..15)
+        uint32_t accNeg = 0, accFar = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int y = k & 3, x = k >> 2;
+            const uint32_t e = lanes_of(p[4 * y + 2 + x], p[4 * y + x], f.laneBias);
+            const uint32_t x2 = lqt_lanes(e, f);
+            accNeg = bitsel(~e, accNeg >> 1, 0x40004000u);   // !Gez
+            accFar = bitsel(~x2, accFar >> 1, 0x80008000u);  // !Lqt
+        }
+        // lanes hold their 8 flags at bits 7..14 (accNeg) and 8..15 (accFar)
+        word1 = prmt(accNeg >> 7, accFar >> 8, 0x6420);
     }
-    // lanes hold their 8 flags at bits 7..14 (accNeg) and 8..15 (accFar)
-    word1 = prmt(accNeg >> 7, accFar >> 8, 0x6420);
 
     // Average colour: the reference's fixed tree of rounded-UP averages (goofy_tc.h:1402-1414),
     // evaluated on complemented bytes so each node is a floor average (3 ops).

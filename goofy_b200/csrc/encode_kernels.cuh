@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 6 : 8) encode_direct_kernel(c
         store_block(dst + o, w0, w1);
     }
     if (MODE == kEtc1 || MODE == kDual) {
-        encode_etc1(p, f, lut, w0, w1);
+        encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
         store_block((MODE == kDual ? dst2 : dst) + o, w0, w1);
     }
 }
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 6 : 8) encode_rows_kernel(con
             store_block(P.dst + o, w0, w1);
         }
         if (MODE == kEtc1 || MODE == kDual) {
-            encode_etc1(p, f, lut, w0, w1);
+            encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
             store_block((MODE == kDual ? P.dst2 : P.dst) + o, w0, w1);
         }
     }
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256, 5) encode_rows_prefetch_kernel(const Enco
             store_block(P.dst + o, w0, w1);
         }
         if (MODE == kEtc1 || MODE == kDual) {
-            encode_etc1(p, f, lut, w0, w1);
+            encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
             store_block((MODE == kDual ? P.dst2 : P.dst) + o, w0, w1);
         }
         if (byNext >= P.bh) break;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kBatchTileX* kBatchTileY)
     const BlockFront f = analyse(p);
     uint32_t w0, w1;
     if (MODE == kDxt1) encode_dxt1(p, f, w0, w1);
-    else encode_etc1(p, f, lut, w0, w1);
+    else encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
     store_block(im.dst + ((uint64_t)by * im.bw + bx) * 8u, w0, w1);
 }
 

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kTmaThreads) encode_tma_kernel(const __grid_co
                 store_block(P.dst + o, w0, w1);
             }
             if (MODE == kEtc1 || MODE == kDual) {
-                encode_etc1(p, f, lut, w0, w1);
+                encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
                 store_block((MODE == kDual ? P.dst2 : P.dst) + o, w0, w1);
             }
         }

@@ -12,6 +12,8 @@
 extern "C" int kernel_math_compress(int codec, unsigned char* result, const unsigned char* input, unsigned width,
                                     unsigned height, unsigned stride)
 {
+    const bool lanePlanes = (codec & 32) != 0;  // ETC1s: the two-pixels-per-register plane scheme (dual-output kernel)
+    codec &= ~32;
     const bool floatRef = (codec & 16) != 0;   // GOOFY_B200_FLOATREF flavours (codec 16 / 17); goofyRef accepts width % 4
     codec &= 15;
     if (width % (floatRef ? 4 : 16)) return -1;
@@ -30,7 +32,8 @@ extern "C" int kernel_math_compress(int codec, unsigned char* result, const unsi
             } else {
                 const gb::BlockFront f = gb::analyse(p);
                 if (codec == 0) gb::encode_dxt1(p, f, w0, w1);
-                else gb::encode_etc1(p, f, lut, w0, w1);
+                else if (lanePlanes) gb::encode_etc1<false>(p, f, lut, w0, w1);
+                else gb::encode_etc1<true>(p, f, lut, w0, w1);
             }
             std::memcpy(result, &w0, 4);
             std::memcpy(result + 4, &w1, 4);

@@ -397,3 +397,28 @@ def test_floatref_flavour_bit_exact_vs_goofyref(codec, oracle):
     torch.cuda.synchronize()
     for i in range(n):
         assert np.array_equal(d_dst[i].cpu().numpy()[: w * h // 2], oracle.compress_float_reference(codec, imgs[i], w, h)[1])
+
+
+def test_images_of_4_gib_and_more_use_64_bit_offsets():
+    """Maximum sizes: a 16384 x 65544 image (4.3 GB) takes the WIDE kernels; its output must equal the
+    same image encoded as two strips (each below 4 GiB, 32-bit offsets) -- the strip-partition property."""
+    free, _ = torch.cuda.mem_get_info()
+    w, h = 16384, 65544
+    need = w * h * 4 + 2 * (w * h // 2) + (1 << 30)
+    if free < need:
+        pytest.skip("not enough device memory")
+    src = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda")
+    gen = torch.Generator(device="cuda"); gen.manual_seed(17)
+    for y0 in range(0, h, 4096):
+        y1 = min(h, y0 + 4096)
+        src[y0:y1] = torch.randint(0, 256, (y1 - y0, w, 4), device="cuda", dtype=torch.uint8, generator=gen)
+    for codec in CODECS:
+        whole = torch.zeros(w * h // 2, dtype=torch.uint8, device="cuda")
+        parts = torch.zeros(w * h // 2, dtype=torch.uint8, device="cuda")
+        assert gb.encode_device(codec, whole, src, w, h, w * 4) == 0
+        h0 = 32768
+        assert gb.encode_device(codec, parts, src, w, h0, w * 4) == 0
+        assert gb.encode_device(codec, parts[(h0 // 4) * (w // 4) * 8:], src[h0:], w, h - h0, w * 4) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(whole, parts)
+        del whole, parts

@@ -26,6 +26,9 @@ def test_kernel_math_on_synthetic(codec, family, kernel_math, oracle):
     img = synth_family(family, 512, 512, seed=1234 + family)
     rc, got = kernel_math(codec, img, 512, 512)
     assert rc == 0 and np.array_equal(got, oracle.compress(codec, img, 512, 512)[1])
+    if codec == ETC1:   # the other selector-plane scheme (used by the dual-output kernel)
+        rc, got = kernel_math(codec | 32, img, 512, 512)
+        assert rc == 0 and np.array_equal(got, oracle.compress(codec, img, 512, 512)[1])
 
 
 @pytest.mark.parametrize("codec", CODECS)
@@ -39,6 +42,8 @@ def test_kernel_math_low_contrast_sweep(codec, kernel_math, oracle):
         img[..., 3] = rng.integers(0, 256, size=(256, 256))
         rc, got = kernel_math(codec, img, 256, 256)
         assert rc == 0 and np.array_equal(got, oracle.compress(codec, img, 256, 256)[1]), spread
+        if codec == ETC1:
+            assert np.array_equal(kernel_math(codec | 32, img, 256, 256)[1], got), spread
 
 
 @pytest.mark.parametrize("codec", CODECS)

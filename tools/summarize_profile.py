@@ -82,9 +82,10 @@ if rep.exists():
     ]
     name_i = hdr.index("Kernel Name")
     with open(out_dir / f"{tag}_ncu_full.md", "w") as f:
-        f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on -k regex:encode_direct -s 9 -c 3 python tools/profile_target.py`\n\n")
-        f.write("One launch each on a device-resident 8192x8192 RGBA8 texture (L2 flushed before each by a 256 MiB memset).\n"
-                "Algorithmic bytes per launch: 268.4 MB read + 33.6 MB written = 302.0 MB (dual: 335.5 MB).\n\n")
+        f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on -k regex:encode_ -s 9 -c 3 python tools/profile_target.py`\n\n")
+        f.write("One launch each over the batch bench.py times: 4 device-resident 8192x8192 RGBA8 textures in one batched launch\n"
+                "(1.07 GB of input per launch, far larger than L2).  Algorithmic bytes per launch: 1073.7 MB read + 134.2 MB\n"
+                "written = 1208.0 MB (dual: 1342.2 MB).\n\n")
         kn = [short(r[name_i]) for r in data]
         f.write("| metric | unit | " + " | ".join(f"`{k}`" for k in kn) + " |\n|---|---|" + "---|" * len(kn) + "\n")
         for w in want:
@@ -92,4 +93,15 @@ if rep.exists():
                 i = hdr.index(w)
                 f.write(f"| {w} | {units[i]} | " + " | ".join(r[i] for r in data) + " |\n")
         f.write("\nTemplate argument: <0,..> DXT1, <1,..> ETC1s, <2,..> both codecs in one pass.\n")
+        # traffic per launch for bench.py's roofline.traffic
+        import json
+        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        traffic = {}
+        for r in data:
+            m = re.search(r"<(\d)", r[name_i])
+            key = {"0": "dxt1", "1": "etc1", "2": "dual"}.get(m.group(1) if m else "", r[name_i][:20])
+            traffic[key] = float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
+        (out_dir / "traffic.json").write_text(json.dumps({"source": f"profiles/{tag}_ncu_full.md", "workload": "4 x 8192x8192 batched launch",
+                                                          "dram_bytes_per_launch": traffic}, indent=1) + "\n")
     print("wrote", out_dir / f"{tag}_ncu_full.md")
