@@ -140,8 +140,12 @@ GB_DEV uint32_t floor_avg4_of_complements(uint32_t a, uint32_t b) { return nor(a
 // word1 = ~(GezPlane | LqtPlane << 16), pixel (x,y) at plane bit ((x^2)<<2)+y.
 // `controlLut[range]` = control byte << 24 (the reference's table, goofy_tc.h:1040-1057).
 // kPixelPlanes selects how the two selector planes are gathered (same result):
-//   true   one pixel at a time on the multiply pipe (3 IDP/IMAD + 2 funnel shifts per pixel) -- relieves the
-//          integer ALU pipe, which is what bounds the ETC1s-only kernel (+1.6 % measured);
+//   true   one pixel at a time on the multiply pipe (IDP/IMAD + 2 funnel shifts per pixel) -- relieves the
+//          integer ALU pipe, which is what bounds the ETC1s-only kernel (+1.6 % measured).  The compiler
+//          rewrites t*t - a*a as (t+a)*(t-a); forcing the single-IMAD form is 30 instructions shorter
+//          and 1.7 % SLOWER (6592 vs 6700 GB/s, A/B in one session), so it is left alone.  A variant that
+//          does the tests in FP32 with .SAT clamps (no integer ALU at all) was exact but spilled and was
+//          3 % slower (6493 GB/s): at ~0.7 instructions/clk/SMSP the kernel is issue-bound as well;
 //   false  two pixels per register as biased u16 lanes (the DXT1 scheme) -- fewer instructions in total, which
 //          is what the dual-output kernel needs (6478 vs 6068 GB/s measured).
 template <bool kPixelPlanes = true>

@@ -1,0 +1,12 @@
+#!/bin/bash
+# A/B of library builds inside one session (same box): alternates the builds twice
+mkdir -p gpurun_out
+for round in 1 2; do
+for lib in "$@"; do
+GOOFY_B200_LIB=$PWD/$lib timeout 600 python bench.py --no-cpu-baseline --no-e2e --steps 200 > gpurun_out/bench_v.json 2> gpurun_out/bench_v.err || tail -3 gpurun_out/bench_v.err
+python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_v.json'))
+print('$lib: DXT1 %.0f GB/s | ETC1 %.0f GB/s | dual %.0f GB/s | per-tex DXT1 %.0f | clk %s' % (d['roofline']['achieved'], d['other_codec']['achieved_gbs_per_gpu'], d['dual_output']['achieved_gbs_per_gpu'], d['per_texture_launch']['achieved_gbs_per_gpu'], d['clocks'].get('sm_mhz')))
+PY
+done; done
