@@ -90,16 +90,35 @@ int check_pointers(const void* src, const void* dst)
     return GOOFY_B200_OK;
 }
 
+// Launch with programmatic stream serialisation (see pdl_wait in encode_kernels.cuh): the kernel's CTAs
+// may be scheduled while the previous kernel of the stream drains, then wait for it before touching memory.
+// GOOFY_B200_PDL=0 turns it off.
+template <typename Kernel>
+int launch_encode(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, const gb::EncodeParams& P)
+{
+    static const bool pdl = []() { const char* e = getenv("GOOFY_B200_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, P);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(e);
+}
+
 template <int MODE, bool PITCHED>
 int launch_direct_grid(const gb::EncodeParams& Q, dim3 grid, dim3 block, cudaStream_t stream)
 {
     // 32-bit in-image offsets unless the image spans 4 GiB or more
     if ((uint64_t)Q.bh * 4u * Q.stride + (uint64_t)Q.bw * 16u < 0xFFFFFFFFull)
-        gb::encode_direct_kernel<MODE, false, PITCHED><<<grid, block, 0, stream>>>(Q);
-    else
-        gb::encode_direct_kernel<MODE, true, PITCHED><<<grid, block, 0, stream>>>(Q);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cuda_rc(cudaGetLastError());
+        return launch_encode(gb::encode_direct_kernel<MODE, false, PITCHED>, grid, block, stream, Q);
+    return launch_encode(gb::encode_direct_kernel<MODE, true, PITCHED>, grid, block, stream, Q);
 }
 
 int sm_count(int dev);
@@ -115,8 +134,7 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     const uint32_t rowGroups = (P.bh + ty - 1u) / ty;
     const int sms = sm_count(dev);
     if (sms <= 0) return GOOFY_B200_E_DEVICE;
-    static const bool prefetch = getenv("GOOFY_B200_ROWS_PREFETCH") != nullptr;  // experiment switch
-    const uint32_t resident = (uint32_t)sms * (prefetch ? 5u : (MODE == gb::kDual ? 6u : 8u));
+    const uint32_t resident = (uint32_t)sms * (MODE == gb::kDual ? 6u : 8u);
     // CTAs walk ~3.5 block rows each on an 8192^2 texture: enough to amortise the per-thread set-up,
     // few enough that CTAs keep retiring and restarting at staggered times (measured: 1x resident
     // 5634, 4x 6111, 14x 5640 GB/s for ETC1s; profiles/r01_rows_grid_sweep.txt).
@@ -126,16 +144,9 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     if (gy > rowGroups) gy = rowGroups;
     if (gy > 65535u) gy = 65535u;
     const dim3 grid(gx, gy, 1), block(tx, ty, 1);
-    const bool narrow = (uint64_t)P.bh * 4u * P.stride + (uint64_t)P.bw * 16u < 0xFFFFFFFFull;
-    if (prefetch) {
-        if (narrow) gb::encode_rows_prefetch_kernel<MODE, false><<<grid, block, 0, stream>>>(P);
-        else gb::encode_rows_prefetch_kernel<MODE, true><<<grid, block, 0, stream>>>(P);
-    } else {
-        if (narrow) gb::encode_rows_kernel<MODE, false><<<grid, block, 0, stream>>>(P);
-        else gb::encode_rows_kernel<MODE, true><<<grid, block, 0, stream>>>(P);
-    }
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cuda_rc(cudaGetLastError());
+    if ((uint64_t)P.bh * 4u * P.stride + (uint64_t)P.bw * 16u < 0xFFFFFFFFull)
+        return launch_encode(gb::encode_rows_kernel<MODE, false>, grid, block, stream, P);
+    return launch_encode(gb::encode_rows_kernel<MODE, true>, grid, block, stream, P);
 }
 
 template <int MODE>

@@ -40,6 +40,14 @@ __global__ void fill_control_lut_kernel()
     g_etc1ControlLut[threadIdx.x] = etc1_control_word(threadIdx.x);
 }
 
+// Programmatic dependent launch: when the host launches with programmatic stream serialisation, the
+// CTAs of this kernel may become resident while the previous kernel on the stream is still draining.
+// `pdl_wait` blocks until that kernel has fully completed and its writes are visible, so ordering is
+// exactly what plain stream order gives -- only the launch latency and the CTA ramp-up are hidden
+// (back-to-back 45 us launches otherwise lose ~7 % to it).  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint4 load_row(const uint8_t* p)
 {
     uint4 v;
@@ -70,6 +78,8 @@ template <int MODE, bool WIDE, bool PITCHED>
 __global__ void __launch_bounds__(256, MODE == 2 ? 6 : 8) encode_direct_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
+    pdl_launch_dependents();
+    pdl_wait();
     if (MODE != kDxt1) {
         // the launcher always uses 256 threads (x a power of two, x*y == 256)
         const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
@@ -121,6 +131,8 @@ template <int MODE, bool WIDE>
 __global__ void __launch_bounds__(256, MODE == 2 ? 6 : 8) encode_rows_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
+    pdl_launch_dependents();
+    pdl_wait();
     if (MODE != kDxt1) {
         const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
         lut[t] = g_etc1ControlLut[t];
@@ -155,58 +167,6 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 6 : 8) encode_rows_kernel(con
             encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
             store_block((MODE == kDual ? P.dst2 : P.dst) + o, w0, w1);
         }
-    }
-}
-
-// Same walk with register double buffering: the four row loads of the NEXT block are issued
-// before the current block is encoded, so every warp always has loads in flight (48 registers,
-// 5 CTAs/SM).
-template <int MODE, bool WIDE>
-__global__ void __launch_bounds__(256, 5) encode_rows_prefetch_kernel(const EncodeParams P)
-{
-    __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
-    if (MODE != kDxt1) {
-        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
-        lut[t] = g_etc1ControlLut[t];
-        __syncthreads();
-    }
-    const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t by = blockIdx.y * blockDim.y + threadIdx.y;
-    if (bx >= P.bw || by >= P.bh) return;
-
-    typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type off_t;
-    const uint32_t rowStep = gridDim.y * blockDim.y;
-    auto load4 = [&](uint32_t row, uint4& a, uint4& b, uint4& c, uint4& d) {
-        const off_t o0 = (off_t)row * (off_t)(4u * P.stride) + (off_t)(bx * 16u);
-        const off_t o1 = o0 + P.stride, o2 = o1 + P.stride, o3 = o2 + P.stride;
-        a = load_row(P.src + o0);
-        b = load_row(P.src + o1);
-        c = load_row(P.src + o2);
-        d = load_row(P.src + o3);
-    };
-    uint4 r0, r1, r2, r3;
-    load4(by, r0, r1, r2, r3);
-#pragma unroll 1
-    for (;;) {
-        const uint32_t byNext = by + rowStep;
-        uint4 n0 = r0, n1 = r1, n2 = r2, n3 = r3;
-        if (byNext < P.bh) load4(byNext, n0, n1, n2, n3);
-        const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
-                                r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
-        const off_t o = ((off_t)by * P.bw + bx) * 8u;
-        const BlockFront f = analyse(p);
-        uint32_t w0, w1;
-        if (MODE == kDxt1 || MODE == kDual) {
-            encode_dxt1(p, f, w0, w1);
-            store_block(P.dst + o, w0, w1);
-        }
-        if (MODE == kEtc1 || MODE == kDual) {
-            encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
-            store_block((MODE == kDual ? P.dst2 : P.dst) + o, w0, w1);
-        }
-        if (byNext >= P.bh) break;
-        by = byNext;
-        r0 = n0; r1 = n1; r2 = n2; r3 = n3;
     }
 }
 

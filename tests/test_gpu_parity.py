@@ -422,3 +422,88 @@ def test_images_of_4_gib_and_more_use_64_bit_offsets():
         torch.cuda.synchronize()
         assert torch.equal(whole, parts)
         del whole, parts
+
+
+def test_concurrent_host_calls_from_threads(oracle):
+    """The drop-in entry points are re-entrant like the reference (pure function, no init call): four host
+    threads encode different images at once through their own thread-local staging pipes."""
+    import threading
+    jobs = []
+    for i in range(8):
+        w, h = 256 + 64 * (i % 3), 128 + 32 * (i % 4)
+        img = synth_family(i % 4, w, h, seed=500 + i)
+        codec = CODECS[i % 2]
+        jobs.append((codec, w, h, aligned_copy(img), oracle.compress(codec, img, w, h)[1]))
+    results = [None] * len(jobs)
+
+    def work(k):
+        codec, w, h, img, _ = jobs[k]
+        out = np.zeros(w * h // 2, dtype=np.uint8)
+        for _ in range(5):
+            rc = HOST_FN[codec](out, img, w, h, w * 4)
+            if rc != 0:
+                break
+        results[k] = (rc, out)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for (codec, w, h, img, want), (rc, out) in zip(jobs, results):
+        assert rc == 0 and np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_stream_order_is_respected_between_launches(codec, oracle):
+    """Back-to-back launches on one stream behave exactly like serial execution (the kernels use programmatic
+    dependent launch to hide launch latency, which must not relax ordering): a later encode into the same
+    destination wins, and an encode sees pixels written by the kernel just before it."""
+    w, h = 2048, 1024
+    a, b = synth_family(0, w, h, seed=1), synth_family(1, w, h, seed=2)
+    want_b = oracle.compress(codec, b, w, h)[1]
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        d_a, d_b = dev(a), dev(b)
+        dst = torch.zeros(w * h // 2, dtype=torch.uint8, device="cuda")
+        scratch = torch.empty_like(d_a)
+        for _ in range(10):
+            assert gb.encode_device(codec, dst, d_a, w, h, w * 4) == 0      # WAW: overwritten below
+            assert gb.encode_device(codec, dst, d_b, w, h, w * 4) == 0
+        got1 = dst.clone()
+        for _ in range(10):
+            scratch.copy_(d_a)                                               # RAW: the encode must see the copy
+            assert gb.encode_device(codec, dst, scratch, w, h, w * 4) == 0
+            scratch.copy_(d_b)
+            assert gb.encode_device(codec, dst, scratch, w, h, w * 4) == 0
+        got2 = dst.clone()
+    stream.synchronize()
+    assert np.array_equal(got1.cpu().numpy(), want_b)
+    assert np.array_equal(got2.cpu().numpy(), want_b)
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_random_shapes_strides_and_alignments(codec, oracle):
+    """Seeded sweep over widths (multiples of 16), heights (multiples of 4), paddings (multiples of 16) and
+    16-byte-aligned base offsets, device and host entry points."""
+    rng = np.random.default_rng(4242 + codec)
+    for _ in range(40):
+        w = 16 * int(rng.integers(1, 40))
+        h = 4 * int(rng.integers(1, 40))
+        pad = 16 * int(rng.integers(0, 9))
+        off = 16 * int(rng.integers(0, 5))
+        stride = w * 4 + pad
+        tight = rng.integers(0, 256, size=(h, w * 4), dtype=np.uint8)
+        buf = np.full(off + h * stride, 0xEE, dtype=np.uint8)
+        view = buf[off:].reshape(h, stride)
+        view[:, : w * 4] = tight
+        want = oracle.compress(codec, tight, w, h)[1]
+        d_buf = dev(buf)
+        d_dst = torch.zeros(w * h // 2 + 16, dtype=torch.uint8, device="cuda")
+        assert gb.encode_device(codec, d_dst[8:], d_buf[off:], w, h, stride) == 0   # 8-byte aligned output
+        torch.cuda.synchronize()
+        assert np.array_equal(d_dst.cpu().numpy()[8: 8 + w * h // 2], want), (w, h, pad, off)
+        assert not d_dst.cpu().numpy()[:8].any() and not d_dst.cpu().numpy()[8 + w * h // 2:].any()
+        host = aligned_copy(buf)
+        out = np.zeros(w * h // 2, dtype=np.uint8)
+        assert HOST_FN[codec](out, host[off:], w, h, stride) == 0 and np.array_equal(out, want)
