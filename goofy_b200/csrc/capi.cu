@@ -134,7 +134,7 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     const uint32_t rowGroups = (P.bh + ty - 1u) / ty;
     const int sms = sm_count(dev);
     if (sms <= 0) return GOOFY_B200_E_DEVICE;
-    const uint32_t resident = (uint32_t)sms * (MODE == gb::kDual ? 6u : 8u);
+    const uint32_t resident = (uint32_t)sms * (MODE == gb::kDual ? (uint32_t)GB_DUAL_CTAS : 8u);
     // CTAs walk ~3.5 block rows each on an 8192^2 texture: enough to amortise the per-thread set-up,
     // few enough that CTAs keep retiring and restarting at staggered times (measured: 1x resident
     // 5634, 4x 6111, 14x 5640 GB/s for ETC1s; profiles/r01_rows_grid_sweep.txt).
@@ -438,6 +438,7 @@ struct HostPipe {
             ready = true;
         }
         if (needIn > capIn) {
+            capIn = 0;  // stays 0 if an allocation below fails, so the next call starts over
             for (int i = 0; i < kSlots; ++i) {
                 if (dIn[i]) cudaFree(dIn[i]);
                 dIn[i] = nullptr;
@@ -446,6 +447,7 @@ struct HostPipe {
             capIn = needIn;
         }
         if (needOut > capOut) {
+            capOut = 0;
             for (int i = 0; i < kSlots; ++i) {
                 if (dOut[i]) cudaFree(dOut[i]);
                 dOut[i] = nullptr;

@@ -20,6 +20,10 @@ namespace gb {
 
 enum Mode : int { kDxt1 = 0, kEtc1 = 1, kDual = 2 };
 
+#ifndef GB_DUAL_CTAS
+#define GB_DUAL_CTAS 6   // resident CTAs per SM the dual-output kernels are compiled for (40 registers)
+#endif
+
 struct EncodeParams {
     const uint8_t* src;
     uint8_t* dst;        // DXT1 (kDxt1, kDual) or ETC1 (kEtc1) blocks
@@ -75,7 +79,7 @@ __device__ __forceinline__ void store_block(uint8_t* p, uint32_t w0, uint32_t w1
 // PITCHED = true adds blockIdx.z * pitch for batches whose images are not back to back (batches
 // that ARE back to back are launched as one tall image, so the common case pays nothing).
 template <int MODE, bool WIDE, bool PITCHED>
-__global__ void __launch_bounds__(256, MODE == 2 ? 6 : 8) encode_direct_kernel(const EncodeParams P)
+__global__ void __launch_bounds__(256, MODE == 2 ? GB_DUAL_CTAS : 8) encode_direct_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     pdl_launch_dependents();
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 6 : 8) encode_direct_kernel(c
 // (indices, control table, constants) is paid once and each further block costs only the
 // pointer bumps -- about 25 fewer instructions per block than one-shot CTAs.
 template <int MODE, bool WIDE>
-__global__ void __launch_bounds__(256, MODE == 2 ? 6 : 8) encode_rows_kernel(const EncodeParams P)
+__global__ void __launch_bounds__(256, MODE == 2 ? GB_DUAL_CTAS : 8) encode_rows_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     pdl_launch_dependents();
