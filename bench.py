@@ -354,6 +354,15 @@ def run_b200_arm(args):
                "h2d_bytes_per_step": size * size * 4, "d2h_bytes_per_step": out_bytes,
                "ms_per_step": ms_e / e2e_steps,
                "api": f"goofy_b200.compress{args.codec.upper()}(result, input, w, h, stride) on pinned host buffers"}
+        # same call with ordinary (pageable) numpy buffers: the library stages them through pinned strips
+        p_src = src[0].cpu().numpy().reshape(-1)
+        p_dst = np.zeros(out_bytes, dtype=np.uint8)
+
+        def e2e_pageable_step():
+            gb.check(host_fn(p_dst, p_src, size, size, stride))
+        ms_p, _ = timed(e2e_pageable_step, e2e_steps, 2)
+        e2e["pageable_buffers"] = {"value": size * size * e2e_steps * world / (ms_p * 1e-3) / 1e6, "unit": "MP/s",
+                                   "ms_per_step": ms_p / e2e_steps}
         # the result must be the same bytes the device-resident path produced
         gb.check(gb.encode_device(codec, dst[0], src[0], size, size, stride))
         torch.cuda.synchronize()

@@ -531,3 +531,24 @@ def test_device_entry_points_are_cuda_graph_capturable(oracle):
     assert gb.kernel_launches() == launches          # replays launch from the graph, not through the library
     for i in range(n):
         assert np.array_equal(d_dst[i].cpu().numpy(), oracle.compress(CODECS[i % 2], imgs[i], w, h)[1])
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_host_api_pinned_and_pageable_buffers(codec, oracle):
+    """Pinned buffers are DMA'd in place; pageable ones are staged through pinned strips by the library's copy
+    threads.  Large enough for several strips (48 MiB in), padded stride, all four pinned/pageable combinations."""
+    w, h, pad = 4096, 3072, 512
+    stride = w * 4 + pad
+    tight = synth_family(1, w, h, seed=77)
+    want = oracle.compress(codec, tight, w, h)[1]
+    padded = np.full((h, stride), 0xAB, dtype=np.uint8)
+    padded[:, : w * 4] = tight.reshape(h, w * 4)
+    pageable_in = aligned_copy(padded)
+    pinned_in = torch.empty(padded.size, dtype=torch.uint8).pin_memory()
+    pinned_in.numpy()[:] = padded.reshape(-1)
+    for src in (pageable_in, pinned_in):
+        for pinned_out in (False, True):
+            out = torch.zeros(w * h // 2, dtype=torch.uint8)
+            out = out.pin_memory() if pinned_out else out
+            assert HOST_FN[codec](out, src, w, h, stride) == 0
+            assert np.array_equal(out.numpy(), want)
