@@ -128,13 +128,13 @@ template <int MODE>
 int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
 {
     uint32_t tx = 32u;
-    while (tx < 256u && tx < P.bw) tx <<= 1;
-    const uint32_t ty = 256u / tx;
+    while (tx < (uint32_t)GB_TPB && tx < P.bw) tx <<= 1;
+    const uint32_t ty = (uint32_t)GB_TPB / tx;
     const uint32_t gx = (P.bw + tx - 1u) / tx;
     const uint32_t rowGroups = (P.bh + ty - 1u) / ty;
     const int sms = sm_count(dev);
     if (sms <= 0) return GOOFY_B200_E_DEVICE;
-    const uint32_t resident = (uint32_t)sms * (MODE == gb::kDual ? (uint32_t)GB_DUAL_CTAS : 8u);
+    const uint32_t resident = (uint32_t)sms * (MODE == gb::kDual ? (uint32_t)GB_DUAL_CTAS : 8u) * (256u / (uint32_t)GB_TPB);
     // CTAs walk ~3.5 block rows each on an 8192^2 texture: enough to amortise the per-thread set-up,
     // few enough that CTAs keep retiring and restarting at staggered times (measured: 1x resident
     // 5634, 4x 6111, 14x 5640 GB/s for ETC1s; profiles/r01_rows_grid_sweep.txt).
@@ -165,10 +165,10 @@ int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream, int
     const bool rows = path == GOOFY_B200_LOAD_DIRECT || (path == GOOFY_B200_LOAD_AUTO && MODE != gb::kDxt1);
     if (nImages == 1u && rows) return launch_rows<MODE>(P, stream, dev);
     // one-shot CTAs (pitched batches): threads: x walks blocks along a row (coalescing), y stacks block rows for narrow images
-    // (x is a power of two and x*y == 256: the kernels rely on exactly 256 threads)
+    // (x is a power of two and x*y == GB_TPB: the kernels rely on exactly GB_TPB threads)
     uint32_t tx = 32u;
-    while (tx < 256u && tx < P.bw) tx <<= 1;
-    const uint32_t ty = 256u / tx;
+    while (tx < (uint32_t)GB_TPB && tx < P.bw) tx <<= 1;
+    const uint32_t ty = (uint32_t)GB_TPB / tx;
     const dim3 block(tx, ty, 1);
     const uint32_t gx = (P.bw + tx - 1u) / tx;
     const uint32_t rowsPerLaunch = 65535u * ty;

@@ -20,6 +20,9 @@ namespace gb {
 
 enum Mode : int { kDxt1 = 0, kEtc1 = 1, kDual = 2 };
 
+#ifndef GB_TPB
+#define GB_TPB 256     // threads per CTA of the direct / row-walking kernels (x a power of two, x*y == GB_TPB)
+#endif
 #ifndef GB_DUAL_CTAS
 #define GB_DUAL_CTAS 6   // resident CTAs per SM the dual-output kernels are compiled for (40 registers)
 #endif
@@ -79,15 +82,16 @@ __device__ __forceinline__ void store_block(uint8_t* p, uint32_t w0, uint32_t w1
 // PITCHED = true adds blockIdx.z * pitch for batches whose images are not back to back (batches
 // that ARE back to back are launched as one tall image, so the common case pays nothing).
 template <int MODE, bool WIDE, bool PITCHED>
-__global__ void __launch_bounds__(256, MODE == 2 ? GB_DUAL_CTAS : 8) encode_direct_kernel(const EncodeParams P)
+__global__ void __launch_bounds__(GB_TPB, (MODE == 2 ? GB_DUAL_CTAS : 8) * 256 / GB_TPB) encode_direct_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     pdl_launch_dependents();
     pdl_wait();
     if (MODE != kDxt1) {
-        // the launcher always uses 256 threads (x a power of two, x*y == 256)
+        // the launcher always uses GB_TPB threads (x a power of two, x*y == GB_TPB)
         const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
-        lut[t] = g_etc1ControlLut[t];
+#pragma unroll
+        for (uint32_t i = t; i < 256u; i += GB_TPB) lut[i] = g_etc1ControlLut[i];
         __syncthreads();
     }
 
@@ -132,14 +136,15 @@ __global__ void __launch_bounds__(256, MODE == 2 ? GB_DUAL_CTAS : 8) encode_dire
 // (indices, control table, constants) is paid once and each further block costs only the
 // pointer bumps -- about 25 fewer instructions per block than one-shot CTAs.
 template <int MODE, bool WIDE>
-__global__ void __launch_bounds__(256, MODE == 2 ? GB_DUAL_CTAS : 8) encode_rows_kernel(const EncodeParams P)
+__global__ void __launch_bounds__(GB_TPB, (MODE == 2 ? GB_DUAL_CTAS : 8) * 256 / GB_TPB) encode_rows_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     pdl_launch_dependents();
     pdl_wait();
     if (MODE != kDxt1) {
         const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
-        lut[t] = g_etc1ControlLut[t];
+#pragma unroll
+        for (uint32_t i = t; i < 256u; i += GB_TPB) lut[i] = g_etc1ControlLut[i];
         __syncthreads();
     }
     const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
