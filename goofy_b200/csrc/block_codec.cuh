@@ -144,8 +144,9 @@ GB_DEV uint32_t floor_avg4_of_complements(uint32_t a, uint32_t b) { return nor(a
 //          integer ALU pipe, which is what bounds the ETC1s-only kernel (+1.6 % measured).  The compiler
 //          rewrites t*t - a*a as (t+a)*(t-a); forcing the single-IMAD form is 30 instructions shorter
 //          and 1.7 % SLOWER (6592 vs 6700 GB/s, A/B in one session), so it is left alone.  A variant that
-//          does the tests in FP32 with .SAT clamps (no integer ALU at all) was exact but spilled and was
-//          3 % slower (6493 GB/s): at ~0.7 instructions/clk/SMSP the kernel is issue-bound as well;
+//          does the tests in FP32 with .SAT clamps (no integer ALU at all, exact, no spills, 277 instructions)
+//          was 3 % slower (6540 GB/s), and a one-IDP form, (e+4qt-3)*(4qt-e)-1, 16 instructions shorter,
+//          was 1 % slower (6710 GB/s): at ~0.76 instructions/clk/SMSP the kernel is issue-bound as well;
 //   false  two pixels per register as biased u16 lanes (the DXT1 scheme) -- fewer instructions in total, which
 //          is what the dual-output kernel needs (6478 vs 6068 GB/s measured).
 template <bool kPixelPlanes = true>
