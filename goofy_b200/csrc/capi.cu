@@ -299,8 +299,10 @@ int launch_tma(void* dst, void* dst2, const void* src, uint32_t width, uint32_t 
     P.nStages = nStages;
     P.tilesX = make_fastdiv(tilesX);
     P.rows = make_fastdiv(P.bh);
-    // persistent CTAs: as many as are resident at once, never more than there are tiles
-    uint32_t grid = (uint32_t)smCount * (uint32_t)ctasPerSm;
+    // CTAs walk a few tiles each: a multiple of what is resident at once (fully persistent CTAs run in
+    // lock-step and are slower, as with the row-walking kernels), never more than there are tiles
+    static const uint32_t gridMult = []() { const char* e = getenv("GOOFY_B200_TMA_GRID_MULT"); const int v = e ? atoi(e) : 8; return v > 0 ? (uint32_t)v : 8u; }();
+    uint32_t grid = (uint32_t)smCount * (uint32_t)ctasPerSm * gridMult;
     if (grid > P.nTiles) grid = P.nTiles;
     gb::encode_tma_kernel<MODE><<<grid, gb::kTmaThreads, smemBytes, stream>>>(map, P);
     g_launches.fetch_add(1, std::memory_order_relaxed);
