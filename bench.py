@@ -97,19 +97,22 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._run_nvml if self.nvml else self._run_smi, daemon=True)
         self.thread.start()
 
-    def _run_nvml(self):
+    def _sample_nvml(self):
         n = self.nvml
-        while not self.stop_flag.is_set():
+        try:
+            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
             try:
-                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
-                try:
-                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                except Exception:
-                    rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                self.samples.append((sm, pw, rs))
+                rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
             except Exception:
-                pass
+                rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.samples.append((sm, pw, rs))
+        except Exception:
+            pass
+
+    def _run_nvml(self):
+        while not self.stop_flag.is_set():
+            self._sample_nvml()
             time.sleep(0.002)
 
     def _run_smi(self):
@@ -127,6 +130,8 @@ class ClockSampler:
         self.stop_flag.set()
         if self.thread is not None:
             self.thread.join(timeout=6)
+        if self.nvml and len(self.samples) < 2:
+            self._sample_nvml()   # very short timed regions: make sure there is at least one reading
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
         sm = [x[0] for x in self.samples]
