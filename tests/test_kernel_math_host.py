@@ -72,3 +72,34 @@ def test_floatref_kernel_math(codec, kernel_math, oracle):
         assert rc == 0 and np.array_equal(got, oracle.compress_float_reference(codec, img, w, h)[1])
     assert kernel_math(16 + codec, splitmix_rgba(20 * 8, seed=1), 20, 8)[0] == 0
     assert kernel_math(16 + codec, splitmix_rgba(64 * 64, seed=1), 18, 8)[0] == -1
+
+
+def test_kernel_math_property_based(kernel_math, oracle):
+    """hypothesis-driven blocks: few distinct values, saturated channels, single-pixel outliers -- the shapes that
+    hit ties (brightness == mid), the range clamp, the to5 edges and the ETC1 table steps."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    levels = st.sampled_from([0, 1, 7, 8, 9, 15, 16, 17, 127, 128, 129, 247, 248, 254, 255])
+    pixel = st.tuples(st.one_of(levels, st.integers(0, 255)), st.one_of(levels, st.integers(0, 255)),
+                      st.one_of(levels, st.integers(0, 255)), st.integers(0, 255))
+    palette = st.lists(pixel, min_size=1, max_size=4)
+
+    @settings(max_examples=300, deadline=None, derandomize=True)
+    @given(pal=palette, picks=st.lists(st.integers(0, 3), min_size=64, max_size=64), jitter=st.integers(0, 3))
+    def run(pal, picks, jitter):
+        # a 16x4 tile = four blocks; every pixel is one of <= 4 palette colours, optionally jittered by +-jitter
+        img = np.zeros((4, 16, 4), dtype=np.int64)
+        for i, k in enumerate(picks):
+            img[i // 16, i % 16] = pal[k % len(pal)]
+        if jitter:
+            img[..., :3] += (np.arange(4 * 16 * 3).reshape(4, 16, 3) * 7919 % (2 * jitter + 1)) - jitter
+        img = np.clip(img, 0, 255).astype(np.uint8)
+        for codec in CODECS:
+            want = oracle.compress(codec, img, 16, 4)[1]
+            assert np.array_equal(kernel_math(codec, img, 16, 4)[1], want)
+            if codec == ETC1:
+                assert np.array_equal(kernel_math(codec | 32, img, 16, 4)[1], want)
+            assert np.array_equal(kernel_math(16 + codec, img, 16, 4)[1], oracle.compress_float_reference(codec, img, 16, 4)[1])
+
+    run()
