@@ -22,10 +22,13 @@ namespace gb {
 
 constexpr int kTmaMaxStages = 8;
 constexpr int kTmaBoxPixels = 256;   // TMA box limit: 256 elements per dimension (u32 element = 1 pixel)
-constexpr int kTmaBoxesPerTile = 4;  // tile = 1024 pixels = 256 blocks wide, one block row high
-constexpr int kTmaThreads = kTmaBoxesPerTile * kTmaBoxPixels / 4;             // 256: one thread per block
+#ifndef GB_TMA_BOXES
+#define GB_TMA_BOXES 2
+#endif
+constexpr int kTmaBoxesPerTile = GB_TMA_BOXES;  // tile = 512 pixels = 128 blocks wide (128-thread CTAs), one block row high
+constexpr int kTmaThreads = kTmaBoxesPerTile * kTmaBoxPixels / 4;             // 128: one thread per block
 constexpr int kTmaBoxBytes = kTmaBoxPixels * 4 * 4;                           // 4 pixel rows x 1 KiB
-constexpr int kTmaStageBytes = kTmaBoxesPerTile * kTmaBoxBytes;               // 16 KiB
+constexpr int kTmaStageBytes = kTmaBoxesPerTile * kTmaBoxBytes;               // 8 KiB
 
 // q = n / d by multiplication: exact for n < 2^24 and d <= 2^16 (m = ceil(2^40 / d)).
 struct FastDiv {
@@ -41,6 +44,7 @@ struct TmaParams {
     uint32_t bw, bh;
     uint32_t nTiles;
     uint32_t nStages;  // depth of the shared-memory tile ring (dynamic smem = nStages * 16 KiB)
+    uint32_t evictFirst;  // 1: loads carry an L2 evict-first policy (streaming data)
     FastDiv tilesX;  // tiles per block row
     FastDiv rows;    // block rows per image
 };
@@ -65,15 +69,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
-// box (c0 pixels, c1 pixel rows, c2 images) -> shared memory, streaming (L2 evict-first)
+// box (c0 pixels, c1 pixel rows, c2 images) -> shared memory, optionally with an L2 evict-first policy
 __device__ __forceinline__ void tma_load_box(uint32_t dstSmem, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t c2,
-                                             uint32_t bar, uint64_t policy)
+                                             uint32_t bar, uint64_t policy, bool hinted)
 {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dstSmem),
-        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
-        : "memory");
+    if (hinted)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+            " [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dstSmem),
+            "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
+            : "memory");
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dstSmem),
+            "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+            : "memory");
 }
 
 template <int MODE>
@@ -84,7 +95,10 @@ __global__ void __launch_bounds__(kTmaThreads) encode_tma_kernel(const __grid_co
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
 
     const uint32_t tid = threadIdx.x;
-    if (MODE != kDxt1) lut[tid] = g_etc1ControlLut[tid];
+    if (MODE != kDxt1) {
+#pragma unroll
+        for (uint32_t i = tid; i < 256u; i += kTmaThreads) lut[i] = g_etc1ControlLut[i];
+    }
     if (tid == 0) {
         for (uint32_t s = 0; s < P.nStages; ++s) mbar_init(smem_addr(&fullBar[s]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -106,7 +120,7 @@ __global__ void __launch_bounds__(kTmaThreads) encode_tma_kernel(const __grid_co
 #pragma unroll 1
         for (uint32_t j = 0; j < nBoxes; ++j)
             tma_load_box(tileBase + stage * kTmaStageBytes + j * kTmaBoxBytes, &map,
-                         (tx * kTmaBoxesPerTile + j) * kTmaBoxPixels, by * 4u, img, bar, policy);
+                         (tx * kTmaBoxesPerTile + j) * kTmaBoxPixels, by * 4u, img, bar, policy, P.evictFirst != 0u);
     };
     if (tid == 0) {
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
