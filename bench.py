@@ -414,8 +414,9 @@ def run_b200_arm(args):
                          "kernel": ("encode_direct_kernel" if codec == gb.DXT1 and args.load_path in ("auto", "oneshot")
                                     else "encode_tma_kernel" if args.load_path == "tma" else "encode_rows_kernel") + f"<{args.codec}>",
                          "bytes_per_launch": bytes_per_launch, "launch_ms": launch_ms,
-                         "like_for_like_ceiling": "tools/membench rows4/nc: 6696 GB/s for an 8:1 read:write stream at 302 MB per launch "
-                                                  "(profiles/r01_membench.txt)"},
+                         "like_for_like_ceiling": "tools/membench (profiles/r01_membench.txt): a trivial-compute kernel with the same "
+                                                  "8:1 read:write access pattern reaches 7115 GB/s at 1.2 GB per launch "
+                                                  "(6696 GB/s at 302 MB); read-only 7355 GB/s"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "per_texture_launch": {"value": value_s, "unit": "MP/s", "launches_per_step": launches_s / side_steps,

@@ -125,11 +125,13 @@ __global__ void __launch_bounds__(256) k_copy(const uint4* src, uint4* dst, size
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) dst[i] = src[i];
 }
 
-int main()
+int main(int argc, char** argv)
 {
-    const uint32_t W = 8192, H = 8192, bw = W / 4, bh = H / 4, stride = W * 4;
+    // default: one 8192x8192 texture per launch (302 MB); "membench 4" = four textures per launch (1.2 GB, bench.py's step)
+    const uint32_t tall = argc > 1 ? (uint32_t)atoi(argv[1]) : 1u;
+    const uint32_t W = 8192, H = 8192 * tall, bw = W / 4, bh = H / 4, stride = W * 4;
     const size_t inBytes = (size_t)W * H * 4, outBytes = inBytes / 8;
-    const int NBUF = 4;
+    const int NBUF = tall > 1 ? 2 : 4;
     uint8_t* src[NBUF]; uint8_t* dst[NBUF];
     for (int i = 0; i < NBUF; ++i) { cudaMalloc(&src[i], inBytes); cudaMalloc(&dst[i], inBytes); cudaMemset(src[i], i + 1, inBytes); }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
