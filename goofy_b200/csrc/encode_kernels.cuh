@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(GB_TPB, (MODE == 2 ? GB_DUAL_CTAS : 8) * 256 /
     if (bx >= P.bw || by >= P.bh) return;
 
     typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type off_t;
-    const off_t o0 = (off_t)by * (off_t)(4u * P.stride) + (off_t)(bx * 16u);
+    const off_t o0 = (off_t)by * ((off_t)4u * P.stride) + (off_t)(bx * 16u);
     const off_t o1 = o0 + P.stride, o2 = o1 + P.stride, o3 = o2 + P.stride;
     const uint8_t* src = P.src;
     uint8_t* dst = P.dst;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(GB_TPB, (MODE == 2 ? GB_DUAL_CTAS : 8) * 256 /
     // otherwise idle multiply pipe) so the loop state stays inside the 32-register budget.
 #pragma unroll 1
     for (; by < P.bh; by += rowStep) {
-        const off_t o0 = (off_t)by * (off_t)(4u * P.stride) + (off_t)(bx * 16u);
+        const off_t o0 = (off_t)by * ((off_t)4u * P.stride) + (off_t)(bx * 16u);
         const off_t o1 = o0 + P.stride, o2 = o1 + P.stride, o3 = o2 + P.stride;
         const uint4 r0 = load_row(P.src + o0);
         const uint4 r1 = load_row(P.src + o1);
