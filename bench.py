@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--codec", choices=["dxt1", "etc1"], default="dxt1")
     ap.add_argument("--size", type=int, default=8192, help="texture width = height")
     ap.add_argument("--batch", type=int, default=4, help="distinct textures per step")
-    ap.add_argument("--load-path", choices=["auto", "direct", "tma", "oneshot"], default="auto",
+    ap.add_argument("--load-path", choices=["auto", "direct", "tma", "oneshot", "async"], default="auto",
                     help="image load layer of the device entry points (see include/goofy_b200.h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -253,7 +253,7 @@ def run_b200_arm(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    gb.set_load_path({"auto": gb.LOAD_AUTO, "direct": gb.LOAD_DIRECT, "tma": gb.LOAD_TMA, "oneshot": gb.LOAD_ONESHOT}[args.load_path])
+    gb.set_load_path({"auto": gb.LOAD_AUTO, "direct": gb.LOAD_DIRECT, "tma": gb.LOAD_TMA, "oneshot": gb.LOAD_ONESHOT, "async": gb.LOAD_ASYNC}[args.load_path])
     codec = gb.DXT1 if args.codec == "dxt1" else gb.ETC1
     size, batch = args.size, args.batch
     stride = size * 4

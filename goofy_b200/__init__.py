@@ -11,7 +11,7 @@ from .api import (DXT1_FLOATREF, ETC1_FLOATREF, goofyRef, decode_device, block_s
                   encode_batch_device, encode_batch_sharded, encode_batch_uniform_device, encode_device,
                   encode_dual_device, encode_host, encode_sharded_host, error_string, kernel_launches,
                   make_descriptors, output_bytes, strip_partition, set_load_path, get_load_path, LOAD_AUTO,
-                  LOAD_DIRECT, LOAD_TMA, LOAD_ONESHOT)
+                  LOAD_DIRECT, LOAD_TMA, LOAD_ONESHOT, LOAD_ASYNC)
 
 __all__ = [
     "DXT1_FLOATREF", "ETC1_FLOATREF", "goofyRef",
@@ -20,5 +20,5 @@ __all__ = [
     "encode_batch_device", "encode_batch_sharded", "encode_batch_uniform_device", "encode_device",
     "encode_dual_device", "encode_host", "encode_sharded_host", "error_string", "kernel_launches",
     "make_descriptors", "output_bytes", "strip_partition", "set_load_path", "get_load_path", "LOAD_AUTO",
-    "LOAD_DIRECT", "LOAD_TMA", "LOAD_ONESHOT",
+    "LOAD_DIRECT", "LOAD_TMA", "LOAD_ONESHOT", "LOAD_ASYNC",
 ]

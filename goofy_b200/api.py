@@ -46,7 +46,7 @@ def kernel_launches() -> int:
     return int(_lib.load().goofy_b200_kernel_launches())
 
 
-LOAD_AUTO, LOAD_DIRECT, LOAD_TMA, LOAD_ONESHOT = 0, 1, 2, 3
+LOAD_AUTO, LOAD_DIRECT, LOAD_TMA, LOAD_ONESHOT, LOAD_ASYNC = 0, 1, 2, 3, 4
 
 
 def set_load_path(path: int) -> int:

@@ -134,7 +134,9 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     const uint32_t rowGroups = (P.bh + ty - 1u) / ty;
     const int sms = sm_count(dev);
     if (sms <= 0) return GOOFY_B200_E_DEVICE;
-    const uint32_t resident = (uint32_t)sms * (MODE == gb::kDual ? (uint32_t)GB_DUAL_CTAS : 8u) * (256u / (uint32_t)GB_TPB);
+    const bool async = g_loadPath.load(std::memory_order_relaxed) == GOOFY_B200_LOAD_ASYNC;
+    const uint32_t resident = async ? (uint32_t)sms * (MODE == gb::kDual ? 5u : 6u)
+                                    : (uint32_t)sms * (MODE == gb::kDual ? (uint32_t)GB_DUAL_CTAS : 8u) * (256u / (uint32_t)GB_TPB);
     // CTAs walk ~3.5 block rows each on an 8192^2 texture: enough to amortise the per-thread set-up,
     // few enough that CTAs keep retiring and restarting at staggered times (measured: 1x resident
     // 5634, 4x 6111, 14x 5640 GB/s for ETC1s; profiles/r01_rows_grid_sweep.txt).
@@ -144,8 +146,11 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     if (gy > rowGroups) gy = rowGroups;
     if (gy > 65535u) gy = 65535u;
     const dim3 grid(gx, gy, 1), block(tx, ty, 1);
-    if ((uint64_t)P.bh * 4u * P.stride + (uint64_t)P.bw * 16u < 0xFFFFFFFFull)
-        return launch_encode(gb::encode_rows_kernel<MODE, false>, grid, block, stream, P);
+    const bool narrow = (uint64_t)P.bh * 4u * P.stride + (uint64_t)P.bw * 16u < 0xFFFFFFFFull;
+    if (async)
+        return narrow ? launch_encode(gb::encode_rows_async_kernel<MODE, false>, grid, block, stream, P)
+                      : launch_encode(gb::encode_rows_async_kernel<MODE, true>, grid, block, stream, P);
+    if (narrow) return launch_encode(gb::encode_rows_kernel<MODE, false>, grid, block, stream, P);
     return launch_encode(gb::encode_rows_kernel<MODE, true>, grid, block, stream, P);
 }
 
@@ -162,7 +167,8 @@ int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream, int
     // one-shot CTAs are marginally faster (6617 vs 6598 GB/s); the ETC1s and dual-output kernels are
     // instruction-bound and gain 4-13 % from row-walking CTAs.
     const int path = g_loadPath.load(std::memory_order_relaxed);
-    const bool rows = path == GOOFY_B200_LOAD_DIRECT || (path == GOOFY_B200_LOAD_AUTO && MODE != gb::kDxt1);
+    const bool rows = path == GOOFY_B200_LOAD_DIRECT || path == GOOFY_B200_LOAD_ASYNC ||
+                      (path == GOOFY_B200_LOAD_AUTO && MODE != gb::kDxt1);
     if (nImages == 1u && rows) return launch_rows<MODE>(P, stream, dev);
     // one-shot CTAs (pitched batches): threads: x walks blocks along a row (coalescing), y stacks block rows for narrow images
     // (x is a power of two and x*y == GB_TPB: the kernels rely on exactly GB_TPB threads)
@@ -853,7 +859,7 @@ uint64_t goofy_b200_kernel_launches(void) { return g_launches.load(std::memory_o
 
 int goofy_b200_set_load_path(int path)
 {
-    if (path < GOOFY_B200_LOAD_AUTO || path > GOOFY_B200_LOAD_ONESHOT) return GOOFY_B200_E_ARGS;
+    if (path < GOOFY_B200_LOAD_AUTO || path > GOOFY_B200_LOAD_ASYNC) return GOOFY_B200_E_ARGS;
     return g_loadPath.exchange(path, std::memory_order_relaxed);
 }
 

@@ -84,6 +84,7 @@ uint64_t goofy_b200_kernel_launches(void);
 #define GOOFY_B200_LOAD_DIRECT 1
 #define GOOFY_B200_LOAD_TMA 2
 #define GOOFY_B200_LOAD_ONESHOT 3 /* DIRECT with one-shot CTAs instead of persistent row-walking CTAs */
+#define GOOFY_B200_LOAD_ASYNC 4   /* row-walking CTAs prefetching the next block row with cp.async into shared memory */
 int goofy_b200_set_load_path(int path);
 int goofy_b200_get_load_path(void);
 

@@ -552,3 +552,31 @@ def test_host_api_pinned_and_pageable_buffers(codec, oracle):
             out = out.pin_memory() if pinned_out else out
             assert HOST_FN[codec](out, src, w, h, stride) == 0
             assert np.array_equal(out.numpy(), want)
+
+
+@pytest.mark.parametrize("path", ["LOAD_DIRECT", "LOAD_ONESHOT", "LOAD_ASYNC", "LOAD_TMA"])
+@pytest.mark.parametrize("codec", CODECS)
+def test_every_load_layer_is_bit_exact(codec, path, oracle):
+    """All selectable load layers (goofy_b200_set_load_path) run the same block arithmetic: identical bytes."""
+    prev = gb.set_load_path(getattr(gb, path))
+    try:
+        for (w, h, pad) in [(16, 4, 0), (272, 36, 0), (1024, 64, 256), (2064, 1028, 64)]:
+            stride = w * 4 + pad
+            tight = splitmix_rgba(w * h, seed=w + h + pad).reshape(h, w * 4)
+            buf = np.full((h, stride), 0xCD, dtype=np.uint8)
+            buf[:, : w * 4] = tight
+            want = oracle.compress(codec, tight, w, h)[1]
+            rc, got = gpu_device(codec, buf, w, h, stride)
+            assert rc == 0 and np.array_equal(got, want), (path, w, h, pad)
+        if codec == DXT1:
+            n, w, h = 3, 528, 40
+            imgs = np.stack([synth_family(i, w, h, seed=60 + i) for i in range(n)])
+            d_a = torch.zeros((n, w * h // 2), dtype=torch.uint8, device="cuda")
+            d_b = torch.zeros((n, w * h // 2), dtype=torch.uint8, device="cuda")
+            assert gb.encode_dual_device(d_a, d_b, dev(imgs), w, h, w * 4, w * h * 4, w * h // 2, n) == 0
+            torch.cuda.synchronize()
+            for i in range(n):
+                assert np.array_equal(d_a[i].cpu().numpy(), oracle.compress(DXT1, imgs[i], w, h)[1])
+                assert np.array_equal(d_b[i].cpu().numpy(), oracle.compress(ETC1, imgs[i], w, h)[1])
+    finally:
+        gb.set_load_path(prev)

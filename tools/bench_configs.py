@@ -38,7 +38,7 @@ def main():
     ap.add_argument("--images", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--load-path", choices=["auto", "direct", "tma", "oneshot"], default="auto")
+    ap.add_argument("--load-path", choices=["auto", "direct", "tma", "oneshot", "async"], default="auto")
     args = ap.parse_args()
 
     rank, local_rank, world = dist_env()
@@ -47,7 +47,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    gb.set_load_path({"auto": gb.LOAD_AUTO, "direct": gb.LOAD_DIRECT, "tma": gb.LOAD_TMA, "oneshot": gb.LOAD_ONESHOT}[args.load_path])
+    gb.set_load_path({"auto": gb.LOAD_AUTO, "direct": gb.LOAD_DIRECT, "tma": gb.LOAD_TMA, "oneshot": gb.LOAD_ONESHOT, "async": gb.LOAD_ASYNC}[args.load_path])
 
     def barrier():
         if world > 1:
