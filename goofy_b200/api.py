@@ -149,6 +149,12 @@ def encode_device(codec: int, d_result, d_input, width: int, height: int, stride
                                                     stride, _stream_ptr(stream)))
 
 
+def encode_relaxed_device(codec: int, d_result, d_input, width: int, height: int, stride: int, stream=None) -> int:
+    """Any width / height (edge blocks replicate the last column / row); result holds ceil(w/4)*ceil(h/4) blocks."""
+    return int(_lib.load().goofy_b200_encode_relaxed_device(codec, _dev_ptr(d_result), _dev_ptr(d_input), width, height,
+                                                            stride, _stream_ptr(stream)))
+
+
 def encode_batch_uniform_device(codec: int, d_result, d_input, width: int, height: int, stride: int,
                                 input_image_pitch: int, result_image_pitch: int, n_images: int, stream=None) -> int:
     return int(_lib.load().goofy_b200_encode_batch_uniform_device(

@@ -934,6 +934,32 @@ int goofy_b200_encode_dual_device(void* d_result_dxt1, void* d_result_etc1, cons
                           result_image_pitch, n_images, (cudaStream_t)stream);
 }
 
+int goofy_b200_encode_relaxed_device(int codec, void* d_result, const void* d_input, uint32_t width, uint32_t height,
+                                     uint32_t stride, void* stream)
+{
+    if (!is_codec(codec)) return GOOFY_B200_E_CODEC;
+    if (width == 0u || height == 0u) return GOOFY_B200_OK;
+    if ((uint64_t)stride < (uint64_t)width * 4u) return GOOFY_B200_E_STRIDE;
+    if (!d_result || !d_input) return GOOFY_B200_E_NULL;
+    if (((uintptr_t)d_input & 3u) != 0u || (stride & 3u) != 0u || ((uintptr_t)d_result & 7u) != 0u) return GOOFY_B200_E_ALIGN;
+    const uint32_t bw = (width + 3u) / 4u, bh = (height + 3u) / 4u;
+    if (bh > 65535u) return GOOFY_B200_E_ARGS;
+    int rc = ensure_device_ready();
+    if (rc != GOOFY_B200_OK) return rc;
+    const dim3 grid((bw + 255u) / 256u, bh, 1);
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint8_t* src = (const uint8_t*)d_input;
+    uint8_t* dst = (uint8_t*)d_result;
+    switch (codec) {
+        case GOOFY_B200_DXT1: gb::encode_relaxed_kernel<gb::kDxt1, 0><<<grid, 256, 0, s>>>(src, dst, width, height, stride); break;
+        case GOOFY_B200_ETC1: gb::encode_relaxed_kernel<gb::kEtc1, 0><<<grid, 256, 0, s>>>(src, dst, width, height, stride); break;
+        case GOOFY_B200_DXT1_FLOATREF: gb::encode_relaxed_kernel<gb::kDxt1, 1><<<grid, 256, 0, s>>>(src, dst, width, height, stride); break;
+        default: gb::encode_relaxed_kernel<gb::kEtc1, 1><<<grid, 256, 0, s>>>(src, dst, width, height, stride); break;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
 int goofy_b200_decode_device(int codec, void* d_rgba, const void* d_blocks, uint32_t width, uint32_t height, uint32_t stride,
                              void* stream)
 {

@@ -283,6 +283,46 @@ __global__ void __launch_bounds__(256) encode_floatref_kernel(const EncodeParams
     store_block(P.dst + (uint64_t)blockIdx.z * P.dstPitch + ((uint64_t)by * P.bw + bx) * 8u, w0, w1);
 }
 
+// Relaxed shapes: any width / height >= 1 and any 4-byte-aligned stride.  Blocks that
+// hang over the right or bottom edge replicate the last column / row (clamp-to-edge), so the output has
+// ceil(w/4) x ceil(h/4) blocks.  Sixteen clamped 32-bit loads per thread instead of four 128-bit ones: this
+// is the convenience path for odd-sized mip levels, not the roofline path.  FLAVOUR 0 = SSE2-exact
+// arithmetic, 1 = float-reference arithmetic; on images the strict entry points accept, the bytes are the same.
+template <int CODEC, int FLAVOUR>
+__global__ void __launch_bounds__(256) encode_relaxed_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                             uint32_t width, uint32_t height, uint32_t stride)
+{
+    __shared__ uint32_t lut[CODEC == kDxt1 ? 1 : 256];
+    if (CODEC != kDxt1) {
+        lut[threadIdx.x] = FLAVOUR ? g_etc1ControlLutRef[threadIdx.x] : g_etc1ControlLut[threadIdx.x];
+        __syncthreads();
+    }
+    const uint32_t bw = (width + 3u) / 4u, bh = (height + 3u) / 4u;
+    const uint32_t bx = blockIdx.x * 256u + threadIdx.x, by = blockIdx.y;
+    if (bx >= bw || by >= bh) return;
+    uint32_t p[16];
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+        const uint32_t row = min(by * 4u + (uint32_t)y, height - 1u);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const uint32_t col = min(bx * 4u + (uint32_t)x, width - 1u);
+            p[4 * y + x] = __ldg(reinterpret_cast<const uint32_t*>(src + (uint64_t)row * stride + (uint64_t)col * 4u));
+        }
+    }
+    uint32_t w0, w1;
+    if (FLAVOUR == 0) {
+        const BlockFront f = analyse(p);
+        if (CODEC == kDxt1) encode_dxt1(p, f, w0, w1);
+        else encode_etc1<true>(p, f, lut, w0, w1);
+    } else {
+        const RefFront f = analyse_ref(p, CODEC == kDxt1 ? 32u : 64u);
+        if (CODEC == kDxt1) encode_dxt1_ref(p, f, w0, w1);
+        else encode_etc1_ref(p, f, lut, w0, w1);
+    }
+    store_block(dst + ((uint64_t)by * bw + bx) * 8u, w0, w1);
+}
+
 // ------------------------------------------------------------------ ragged batches
 // Images of different shapes in one launch.  The host sorts nothing: it uploads the
 // descriptors plus an exclusive prefix sum of per-image CTA counts; each CTA finds its

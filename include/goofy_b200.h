@@ -109,6 +109,13 @@ int goofy_b200_encode_host(int codec, void* result, const void* input, uint32_t 
 int goofy_b200_encode_device(int codec, void* d_result, const void* d_input, uint32_t width, uint32_t height,
                              uint32_t stride, void* stream);
 
+/* Relaxed shapes (beyond the reference, which rejects them): any width and height >= 1, stride and input only
+ * 4-byte aligned.  Blocks overhanging the right / bottom edge replicate the last column / row, so the result
+ * holds ceil(width/4) * ceil(height/4) blocks.  On shapes the strict entry points accept, the bytes are identical.
+ * Meant for odd-sized mip levels; it uses scalar loads and is not the bandwidth-optimal path. */
+int goofy_b200_encode_relaxed_device(int codec, void* d_result, const void* d_input, uint32_t width, uint32_t height,
+                                     uint32_t stride, void* stream);
+
 /* n images of one shape laid out at fixed pitches (bytes) from d_input / d_result. */
 int goofy_b200_encode_batch_uniform_device(int codec, void* d_result, const void* d_input, uint32_t width,
                                            uint32_t height, uint32_t stride, uint64_t input_image_pitch,

@@ -56,6 +56,13 @@ inline int encode(Codec codec, void* dResult, const void* dInput, uint32_t width
     return goofy_b200_encode_device(codec, dResult, dInput, width, height, stride, stream);
 }
 
+// Any width / height: edge blocks replicate the last column / row; result holds ceil(w/4)*ceil(h/4) blocks.
+inline int encodeRelaxed(int codec, void* dResult, const void* dInput, uint32_t width, uint32_t height, uint32_t stride,
+                         void* stream = nullptr)
+{
+    return goofy_b200_encode_relaxed_device(codec, dResult, dInput, width, height, stride, stream);
+}
+
 // n images of one shape at fixed pitches.
 inline int encodeBatch(Codec codec, void* dResult, const void* dInput, uint32_t width, uint32_t height, uint32_t stride,
                        uint64_t inputImagePitch, uint64_t resultImagePitch, uint32_t nImages, void* stream = nullptr)

@@ -580,3 +580,35 @@ def test_every_load_layer_is_bit_exact(codec, path, oracle):
                 assert np.array_equal(d_b[i].cpu().numpy(), oracle.compress(ETC1, imgs[i], w, h)[1])
     finally:
         gb.set_load_path(prev)
+
+
+@pytest.mark.parametrize("codec", CODECS)
+@pytest.mark.parametrize("flavour", ["sse2", "floatref"])
+def test_relaxed_shapes_edge_replication(codec, flavour, oracle):
+    """Row N4: any width / height.  Expected output = the strict encoder applied to the image padded by
+    replicating its last column / row up to the next legal size, cropped to ceil(w/4) x ceil(h/4) blocks."""
+    rng = np.random.default_rng(99)
+    gcodec = codec if flavour == "sse2" else {DXT1: gb.DXT1_FLOATREF, ETC1: gb.ETC1_FLOATREF}[codec]
+    for (w, h) in [(1, 1), (3, 5), (4, 4), (17, 9), (30, 31), (64, 64), (100, 37), (259, 6), (1025, 3)]:
+        img = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+        stride = w * 4
+        bw, bh = (w + 3) // 4, (h + 3) // 4
+        pw, ph = (w + 15) // 16 * 16, bh * 4
+        padded = np.pad(img, ((0, ph - h), (0, pw - w), (0, 0)), mode="edge")
+        if flavour == "sse2":
+            full = oracle.compress(codec, padded, pw, ph)[1]
+        else:
+            full = oracle.compress_float_reference(codec, padded, pw, ph)[1]
+        want = full.reshape(ph // 4, pw // 4, 8)[:, :bw].reshape(-1)
+        d_dst = torch.zeros(bw * bh * 8, dtype=torch.uint8, device="cuda")
+        assert gb.encode_relaxed_device(gcodec, d_dst, dev(img), w, h, stride) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(d_dst.cpu().numpy(), want), (w, h)
+    # on a strict shape the relaxed path gives the strict path's bytes
+    img = synth_family(1, 256, 64)
+    d_dst = torch.zeros(256 * 64 // 2, dtype=torch.uint8, device="cuda")
+    assert gb.encode_relaxed_device(gcodec, d_dst, dev(img), 256, 64, 1024) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_dst.cpu().numpy(), gpu_device(gcodec, img, 256, 64)[1])
+    assert gb.encode_relaxed_device(gcodec, d_dst, dev(img), 0, 0, 0) == 0
+    assert gb.encode_relaxed_device(gcodec, d_dst, dev(img), 10, 10, 36) == -5
