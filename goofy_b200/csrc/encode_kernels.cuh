@@ -75,6 +75,25 @@ __device__ __forceinline__ void store_block(uint8_t* p, uint32_t w0, uint32_t w1
     asm volatile(GB_STORE_PTX " [%0], {%1,%2};" ::"l"(p), "r"(w0), "r"(w1) : "memory");
 }
 
+// Encode the 16 pixels of one block in MODE and write the 8-byte result(s).
+template <int MODE>
+__device__ __forceinline__ void encode_and_store(const uint4& r0, const uint4& r1, const uint4& r2, const uint4& r3,
+                                                 const uint32_t* lut, uint8_t* dst, uint8_t* dst2)
+{
+    const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
+                            r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+    const BlockFront f = analyse(p);
+    uint32_t w0, w1;
+    if (MODE == kDxt1 || MODE == kDual) {
+        encode_dxt1(p, f, w0, w1);
+        store_block(dst, w0, w1);
+    }
+    if (MODE == kEtc1 || MODE == kDual) {
+        encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
+        store_block(MODE == kDual ? dst2 : dst, w0, w1);
+    }
+}
+
 // 8 resident CTAs per SM (32 registers) for the single-codec kernels, 6 for the dual-output one.
 // WIDE = false: every byte offset inside one image fits 32 bits (the launcher checks), which
 // keeps the address arithmetic to a handful of 32-bit ops; WIDE = true is the same kernel with
@@ -114,20 +133,8 @@ __global__ void __launch_bounds__(GB_TPB, (MODE == 2 ? GB_DUAL_CTAS : 8) * 256 /
     const uint4 r1 = load_row(src + o1);
     const uint4 r2 = load_row(src + o2);
     const uint4 r3 = load_row(src + o3);
-    const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
-                            r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
-
     const off_t o = ((off_t)by * P.bw + bx) * 8u;
-    const BlockFront f = analyse(p);
-    uint32_t w0, w1;
-    if (MODE == kDxt1 || MODE == kDual) {
-        encode_dxt1(p, f, w0, w1);
-        store_block(dst + o, w0, w1);
-    }
-    if (MODE == kEtc1 || MODE == kDual) {
-        encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
-        store_block((MODE == kDual ? dst2 : dst) + o, w0, w1);
-    }
+    encode_and_store<MODE>(r0, r1, r2, r3, lut, dst + o, MODE == kDual ? dst2 + o : nullptr);
 }
 
 // Persistent variant for single images and back-to-back batches: the grid is sized to what is
@@ -163,19 +170,8 @@ __global__ void __launch_bounds__(GB_TPB, (MODE == 2 ? GB_DUAL_CTAS : 8) * 256 /
         const uint4 r1 = load_row(P.src + o1);
         const uint4 r2 = load_row(P.src + o2);
         const uint4 r3 = load_row(P.src + o3);
-        const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
-                                r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
         const off_t o = ((off_t)by * P.bw + bx) * 8u;
-        const BlockFront f = analyse(p);
-        uint32_t w0, w1;
-        if (MODE == kDxt1 || MODE == kDual) {
-            encode_dxt1(p, f, w0, w1);
-            store_block(P.dst + o, w0, w1);
-        }
-        if (MODE == kEtc1 || MODE == kDual) {
-            encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
-            store_block((MODE == kDual ? P.dst2 : P.dst) + o, w0, w1);
-        }
+        encode_and_store<MODE>(r0, r1, r2, r3, lut, P.dst + o, MODE == kDual ? P.dst2 + o : nullptr);
     }
 }
 
@@ -231,19 +227,8 @@ __global__ void __launch_bounds__(GB_TPB, MODE == 2 ? 5 : 6) encode_rows_async_k
         cp_async_commit();          // (possibly empty) group: keeps "all but the newest" == the current stage
         cp_async_wait<1>();
         const uint4 r0 = ring[stage][0][t], r1 = ring[stage][1][t], r2 = ring[stage][2][t], r3 = ring[stage][3][t];
-        const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
-                                r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
         const off_t o = ((off_t)by * P.bw + bx) * 8u;
-        const BlockFront f = analyse(p);
-        uint32_t w0, w1;
-        if (MODE == kDxt1 || MODE == kDual) {
-            encode_dxt1(p, f, w0, w1);
-            store_block(P.dst + o, w0, w1);
-        }
-        if (MODE == kEtc1 || MODE == kDual) {
-            encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
-            store_block((MODE == kDual ? P.dst2 : P.dst) + o, w0, w1);
-        }
+        encode_and_store<MODE>(r0, r1, r2, r3, lut, P.dst + o, MODE == kDual ? P.dst2 + o : nullptr);
         if (byNext >= P.bh) break;
         by = byNext;
         stage ^= 1u;
@@ -366,13 +351,7 @@ __global__ void __launch_bounds__(kBatchTileX* kBatchTileY)
     const uint4 r1 = load_row(s + im.stride);
     const uint4 r2 = load_row(s + 2ull * im.stride);
     const uint4 r3 = load_row(s + 3ull * im.stride);
-    const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
-                            r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
-    const BlockFront f = analyse(p);
-    uint32_t w0, w1;
-    if (MODE == kDxt1) encode_dxt1(p, f, w0, w1);
-    else encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
-    store_block(im.dst + ((uint64_t)by * im.bw + bx) * 8u, w0, w1);
+    encode_and_store<MODE>(r0, r1, r2, r3, lut, im.dst + ((uint64_t)by * im.bw + bx) * 8u, nullptr);
 }
 
 }  // namespace gb

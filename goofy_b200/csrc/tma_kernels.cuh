@@ -150,19 +150,8 @@ __global__ void __launch_bounds__(kTmaThreads) encode_tma_kernel(const __grid_co
 
         const uint32_t bx = tx * kTmaThreads + tid;
         if (bx < P.bw) {
-            const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
-                                    r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
             const uint64_t o = (uint64_t)img * P.dstPitch + ((uint64_t)by * P.bw + bx) * 8u;
-            const BlockFront f = analyse(p);
-            uint32_t w0, w1;
-            if (MODE == kDxt1 || MODE == kDual) {
-                encode_dxt1(p, f, w0, w1);
-                store_block(P.dst + o, w0, w1);
-            }
-            if (MODE == kEtc1 || MODE == kDual) {
-                encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
-                store_block((MODE == kDual ? P.dst2 : P.dst) + o, w0, w1);
-            }
+            encode_and_store<MODE>(r0, r1, r2, r3, lut, P.dst + o, MODE == kDual ? P.dst2 + o : nullptr);
         }
     }
 }
