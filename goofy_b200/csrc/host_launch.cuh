@@ -49,11 +49,15 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     const bool async = g_loadPath.load(std::memory_order_relaxed) == GOOFY_B200_LOAD_ASYNC;
     const uint32_t resident = async ? (uint32_t)sms * (MODE == gb::kDual ? 5u : 6u)
                                     : (uint32_t)sms * (MODE == gb::kDual ? (uint32_t)GB_DUAL_CTAS : 8u) * (256u / (uint32_t)GB_TPB);
-    // CTAs walk ~3.5 block rows each on an 8192^2 texture: enough to amortise the per-thread set-up,
-    // few enough that CTAs keep retiring and restarting at staggered times (measured: 1x resident
-    // 5634, 4x 6111, 14x 5640 GB/s for ETC1s; profiles/r01_rows_grid_sweep.txt).
-    static const uint32_t gyMult = []() { const char* e = getenv("GOOFY_B200_ROWS_GY_MULT"); const int v = e ? atoi(e) : 4; return v > 0 ? (uint32_t)v : 4u; }();
-    uint32_t gy = (uint32_t)(((uint64_t)resident * gyMult) / gx);
+    // Each CTA walks a few block rows: enough to amortise the per-thread set-up, few enough that CTAs keep
+    // retiring and restarting at staggered times (fully persistent CTAs run in lock-step and are 10 % slower;
+    // profiles/r01_rows_grid_sweep.txt).  Never fewer CTAs than one resident wave.
+    // Measured on the batched 4 x 8192^2 launch: ETC1s 6915 / 7011 / 7010 / 6966 / 6892 GB/s at 2 / 3 / 4 / 6 / 8 rows
+    // per CTA; dual-output 5835 / 5932 / 6055 / 6193 / 6293.
+    static const uint32_t rowsEnv = []() { const char* e = getenv("GOOFY_B200_ROWS_PER_CTA"); const int v = e ? atoi(e) : 0; return v > 0 ? (uint32_t)v : 0u; }();
+    const uint32_t rowsPerCta = rowsEnv ? rowsEnv : (MODE == gb::kDual ? 8u : 4u);
+    uint32_t gy = (rowGroups + rowsPerCta - 1u) / rowsPerCta;
+    if (gy < resident / gx) gy = resident / gx;
     if (gy == 0u) gy = 1u;
     if (gy > rowGroups) gy = rowGroups;
     if (gy > 65535u) gy = 65535u;
