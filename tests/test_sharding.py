@@ -44,8 +44,11 @@ def test_batch_partition_is_balanced_and_complete():
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    for k in list(os.environ):   # a launcher's rendezvous settings must not leak into this private group
+        if k.startswith(("TORCHELASTIC", "TORCH_NCCL", "GROUP_", "ROLE_")) or k in ("MASTER_ADDR", "MASTER_PORT", "RANK",
+                                                                                    "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE"):
+            os.environ.pop(k, None)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     # what bench.py does with its per-rank device time: barrier, then MAX over ranks; shards are disjoint
     dist.barrier()
     t = torch.tensor([10.0 + 5.0 * rank], dtype=torch.float64)
@@ -57,6 +60,7 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.timeout(240)
 def test_world_size_2_gloo_timing_reduction_and_disjoint_shards():
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
