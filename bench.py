@@ -144,6 +144,30 @@ class ClockSampler:
                 "reasons": [name for name, bit in self.REASONS if bits & bit]}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """One process per GPU: run on (and first-touch pinned host buffers on) the CPUs NVML reports as local to
+    this rank's GPU, so the host<->device copies of the e2e leg do not cross sockets.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = local_rank
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            idx = int(vis.split(",")[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {idx}"
+    except Exception as e:  # containers often hide the topology: keep the default affinity
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 # ----------------------------------------------------------------------------- synthetic input
 def fill_texture_device(torch, t, seed: int):
     """Photo-like family S1 of SURVEY.md 8(d) (gradient + 4-bit noise), generated on the device:
@@ -249,6 +273,7 @@ def run_b200_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
+    numa = bind_to_gpu_numa_node(local_rank) if distributed else None
     if distributed:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -408,7 +433,8 @@ def run_b200_arm(args):
                        "l2": f"inputs larger than L2: every step streams {batch} distinct {size * size * 4 >> 20} MiB textures "
                              f"({int(px_per_step * BYTES_PER_PIXEL) >> 20} MiB per step vs 126 MB of L2)",
                        "load_path": args.load_path,
-                       "sharding": "one batch per rank, no collectives" if world > 1 else "single GPU"},
+                       "sharding": "one batch per rank, no collectives" if world > 1 else "single GPU",
+                       "cpu_binding": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "kernel": ("encode_direct_kernel" if codec == gb.DXT1 and args.load_path in ("auto", "oneshot")
