@@ -24,6 +24,7 @@ namespace gb {
 
 constexpr uint32_t kLuma = 0x00010201u;   // dp4a weights for bytes (R,G,B,A): R + 2G + B
 constexpr uint32_t kLuma2 = 0x00020402u;  // twice that
+constexpr uint32_t kLumaNeg = 0x00FFFEFFu;  // signed bytes (-1, -2, -1, 0): minus that
 
 // min / max of 16 words, two u16 lanes each, in 8 three-input ops
 template <bool kMax>
@@ -51,6 +52,10 @@ struct BlockFront {
     uint32_t mid;         // avg(minY, maxY)                      goofy_tc.h:1179
     uint32_t laneBias;    // dp4a accumulator that makes lane = (R+2G+B+3) - 4*mid + 0x4000
     uint32_t kLo, kHi;    // packed add constants: bit15 of (lane + kLo) <=> e >= 4 - 4qt, of (lane + kHi) <=> e >= 4qt
+    // flag-byte scheme: per-lane biases (both lanes) that put a threshold flag into bit 15 of Y4 = R+2G+B (+ bias) resp. bias - Y4
+    uint32_t fbG;         // Y4 + fbG : bit15 <=> e >= 0
+    uint32_t fbB;         // Y4 + fbB : bit15 <=> e >= 4qt
+    uint32_t fbNa;        // fbNa - Y4: bit15 <=> e < 4 - 4qt
     // single-pixel form used by the ETC1s planes (everything on the multiply pipe):
     uint32_t cE;          // dp4a(pixel, kLuma,  cE) = e            -> bit31 <=> !Gez
     uint32_t cT;          // dp4a(pixel, kLuma2, cT) = t = 2e - 3
@@ -83,6 +88,10 @@ GB_DEV BlockFront analyse(const uint32_t (&p)[16])
     f.laneBias = 0x4003u - (f.mid << 2);
     f.kLo = (0x3FFCu + q4) * 0x10001u;
     f.kHi = (0x4000u - q4) * 0x10001u;
+    // e = Y4 + 3 - 4 mid; every biased lane stays inside 1..0xFFFE, so the two lanes never exchange a carry
+    f.fbG = (0x8003u - (f.mid << 2)) * 0x10001u;
+    f.fbB = (0x8003u - (f.mid << 2) - q4) * 0x10001u;
+    f.fbNa = (0x8000u + (f.mid << 2) - q4) * 0x10001u;
     f.cE = 3u - (f.mid << 2);
     f.cT = 2u * f.cE - 3u;
     const uint32_t a = 2u * q4 - 5u;   // 8qt - 5, 19..763
@@ -100,11 +109,81 @@ GB_DEV uint32_t lanes_of(uint32_t a, uint32_t b, uint32_t laneBias)
 // bit15 of each lane <=> Lqt (|Y - mid| < qt)
 GB_DEV uint32_t lqt_lanes(uint32_t e, const BlockFront& f) { return (e + f.kLo) ^ (e + f.kHi); }
 
+// How the per-pixel flags (Gez, Lqt) are gathered into the output words.  All three give the same bits.
+//   kSelLanes      two pixels per register as biased u16 lanes, shift-and-insert accumulators (integer ALU pipe)
+//   kSelPixels     one pixel at a time on the multiply pipe, one funnel shift per flag (ETC1s planes only)
+//   kSelFlagBytes  lanes as above, but the flags leave the lanes as 0x00 / 0xFF BYTES (one sign-replicating
+//                  PRMT per four flags) and are weighted into place by IDP.4A on the multiply pipe: 12 integer-ALU
+//                  instructions per block instead of 32-50, and the same twelve flag words feed both codecs.
+enum Selectors : int { kSelLanes = 0, kSelPixels = 1, kSelFlagBytes = 2 };
+
+// Flag-byte scheme.  Per pixel three threshold flags, each the sign bit of a u16 lane (e = S - 4*mid):
+//   G  = e >= 0        NA = e < 4 - 4qt        B = e >= 4qt          (NA and B exclude each other; B implies G)
+// so that   !Gez = 1 - G,   Lqt = 1 - NA - B,   !Lqt = NA + B.
+// Row y is walked as two pairs, (x=0,1) and (x=2,3); per row three flag words:
+//   outerL / outerR = bytes (B_lo, B_hi, NA_lo, NA_hi) of the left / right pair,   gez = bytes (G_0, G_1, G_2, G_3).
+// dp4a_su subtracts the weight of every set flag, hence the accumulators count DOWN from all-ones:
+//   DXT1 index byte of row y = 255 - sum_x 4^x (2 NA + 2 B + G)                      (2*Lqt + !Gez per pixel)
+//   ETC1 planes, pixel (x,y) at bit ((x^2)<<2)+y: x in {2,3} fills plane byte 0, x in {0,1} plane byte 1, with
+//   weights 2^y and 2^(4+y) inside the byte; the !Gez plane counts down from 0xFF per byte, the !Lqt plane up.
+// The IDP weights live in constant memory on the device: the compiler then keeps them in uniform registers
+// across the row loop of the kernels instead of re-creating each one (a UMOV apiece) for every block.
+#if defined(__CUDACC__)
+#define GB_WEIGHT_TABLE __constant__
+#else
+#define GB_WEIGHT_TABLE static const
+#endif
+GB_WEIGHT_TABLE uint32_t kFlagWeights[15] = {
+    0x40100401u, 0x08020802u, 0x80208020u,                                  // DXT1: gez, outerL, outerR
+    0x10011001u << 0, 0x10011001u << 1, 0x10011001u << 2, 0x10011001u << 3,  // ETC1 !Lqt plane, row y
+    0x00001001u << 0, 0x00001001u << 1, 0x00001001u << 2, 0x00001001u << 3,  // ETC1 !Gez plane byte 1 (x = 0,1), row y
+    0x10010000u << 0, 0x10010000u << 1, 0x10010000u << 2, 0x10010000u << 3,  // ETC1 !Gez plane byte 0 (x = 2,3), row y
+};
+
+template <bool kDxt, bool kEtc>
+GB_DEV void selectors_from_flag_bytes(const uint32_t (&p)[16], const BlockFront& f, uint32_t& dxtWord1, uint32_t& etcWord1)
+{
+    uint32_t idx = 0xFFu;
+    uint32_t far0 = 0, far1 = 0, neg0 = 0xFFu, neg1 = 0xFFu;
+#pragma unroll
+    for (int y = 3; y >= 0; --y) {
+        uint32_t b[2], na[2], g[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            // three biased copies of the pair's brightness lanes, each straight out of the multiply pipe
+            // (no separate adds): low lane = pixel x = 2h, high lane = pixel x = 2h + 1
+            const uint32_t lo = p[4 * y + 2 * h], hi = p[4 * y + 2 * h + 1];
+            const uint32_t t = dp4a(hi, kLuma, 0u);
+            g[h] = dp4a(lo, kLuma, t * 0x10000u + f.fbG);
+            b[h] = dp4a(lo, kLuma, t * 0x10000u + f.fbB);
+            na[h] = dp4a_neg(lo, kLumaNeg, t * 0xFFFF0000u + f.fbNa);
+        }
+        const uint32_t outerL = sign_bytes<0xFDB9>(b[0], na[0]);
+        const uint32_t outerR = sign_bytes<0xFDB9>(b[1], na[1]);
+        const uint32_t gez = sign_bytes<0xFDB9>(g[0], g[1]);
+        if (kDxt) {
+            if (y != 3) idx = idx * 256u + 0xFFu;
+            idx = dp4a_su(gez, kFlagWeights[0], idx);
+            idx = dp4a_su(outerL, kFlagWeights[1], idx);
+            idx = dp4a_su(outerR, kFlagWeights[2], idx);
+        }
+        if (kEtc) {
+            far1 = dp4a_su(outerL, kFlagWeights[3 + y], far1);
+            far0 = dp4a_su(outerR, kFlagWeights[3 + y], far0);
+            neg1 = dp4a_su(gez, kFlagWeights[7 + y], neg1);
+            neg0 = dp4a_su(gez, kFlagWeights[11 + y], neg0);
+        }
+    }
+    dxtWord1 = idx;
+    // far0/far1 hold MINUS the plane bytes
+    etcWord1 = (far1 * 256u + far0) * 0xFFFF0000u + (neg1 * 256u + neg0);
+}
+
 // ---------------------------------------------------------------------------------------- DXT1
 // Output (goofy_tc.h:1276-1357): word0 = c0 | c1 << 16 with c0 = max corner 565 | 0x20,
 // c1 = min corner 565 (both with the green LSB cleared); word1 = 2 bits per pixel, row major,
 // bit0 = !Gez, bit1 = Lqt.
-GB_DEV void encode_dxt1(const uint32_t (&p)[16], const BlockFront& f, uint32_t& word0, uint32_t& word1)
+GB_DEV uint32_t dxt1_indices_lanes(const uint32_t (&p)[16], const BlockFront& f)
 {
     // low lane walks pixels 0..7, high lane pixels 8..15; each step pushes 2 bits per lane
     uint32_t acc = 0;
@@ -115,8 +194,11 @@ GB_DEV void encode_dxt1(const uint32_t (&p)[16], const BlockFront& f, uint32_t& 
         const uint32_t z = bitsel(x, ~e, 0x80008000u);  // bit15 = Lqt, bit14 = !Gez
         acc = bitsel(z, acc >> 2, 0xC000C000u);
     }
-    word1 = acc;
+    return acc;
+}
 
+GB_DEV uint32_t dxt1_endpoints(const BlockFront& f)
+{
     // 888 -> 565 for both corners at once: low lane = max corner, high lane = min corner.
     // to5 sits in the top 5 bits of a lane holding (max(v,1)-1) << 8.
     uint32_t rr = prmt(f.mxRB, f.mnRB, 0x5010);  // (0, maxR, 0, minR)
@@ -127,7 +209,19 @@ GB_DEV void encode_dxt1(const uint32_t (&p)[16], const BlockFront& f, uint32_t& 
     // the odd constant also sets bit 16, which the >> 11 below turns into c0's forced green LSB (0x20)
     bb = max2_u16x2(bb, 0x01000100u) - 0x00FF0100u;
     const uint32_t rg = bitsel(rr, gg >> 5, 0xF800F800u);
-    word0 = bitsel(rg, bb >> 11, 0xFFC0FFC0u);
+    return bitsel(rg, bb >> 11, 0xFFC0FFC0u);
+}
+
+template <int SEL = kSelLanes>
+GB_DEV void encode_dxt1(const uint32_t (&p)[16], const BlockFront& f, uint32_t& word0, uint32_t& word1)
+{
+    if (SEL == kSelFlagBytes) {
+        uint32_t unused;
+        selectors_from_flag_bytes<true, false>(p, f, word1, unused);
+    } else {
+        word1 = dxt1_indices_lanes(p, f);
+    }
+    word0 = dxt1_endpoints(f);
 }
 
 // ---------------------------------------------------------------------------------------- ETC1s
@@ -139,25 +233,25 @@ GB_DEV uint32_t floor_avg4_of_complements(uint32_t a, uint32_t b) { return nor(a
 // Output (goofy_tc.h:1358-1493): word0 = R5<<3 | G5<<11 | B5<<19 | control<<24;
 // word1 = ~(GezPlane | LqtPlane << 16), pixel (x,y) at plane bit ((x^2)<<2)+y.
 // `controlLut[range]` = control byte << 24 (the reference's table, goofy_tc.h:1040-1057).
-// kPixelPlanes selects how the two selector planes are gathered (same result):
-//   true   one pixel at a time on the multiply pipe (IDP/IMAD + 2 funnel shifts per pixel) -- relieves the
+// SEL selects how the two selector planes are gathered (same result, see `Selectors`):
+//   kSelPixels  one pixel at a time on the multiply pipe (IDP/IMAD + 2 funnel shifts per pixel) -- relieves the
 //          integer ALU pipe, which is what bounds the ETC1s-only kernel (+1.6 % measured).  The compiler
 //          rewrites t*t - a*a as (t+a)*(t-a); forcing the single-IMAD form is 30 instructions shorter
 //          and 1.7 % SLOWER (6592 vs 6700 GB/s, A/B in one session), so it is left alone.  A variant that
 //          does the tests in FP32 with .SAT clamps (no integer ALU at all, exact, no spills, 277 instructions)
 //          was 3 % slower (6540 GB/s), and a one-IDP form, (e+4qt-3)*(4qt-e)-1, 16 instructions shorter,
 //          was 1 % slower (6710 GB/s): at ~0.76 instructions/clk/SMSP the kernel is issue-bound as well;
-//   false  two pixels per register as biased u16 lanes (the DXT1 scheme) -- fewer instructions in total, which
-//          is what the dual-output kernel needs (6478 vs 6068 GB/s measured).
-template <bool kPixelPlanes = true>
-GB_DEV void encode_etc1(const uint32_t (&p)[16], const BlockFront& f, const uint32_t* controlLut, uint32_t& word0,
-                        uint32_t& word1)
+//   kSelLanes   two pixels per register as biased u16 lanes (the DXT1 scheme) -- fewer instructions in total
+//          (dual-output kernel: 6478 vs 6068 GB/s measured).
+//   kSelFlagBytes  see selectors_from_flag_bytes.
+template <int SEL>
+GB_DEV uint32_t etc1_planes(const uint32_t (&p)[16], const BlockFront& f)
 {
     // The two selector planes, one pixel at a time, entirely on the multiply pipe plus one funnel
     // shift per flag: e = S - 4*mid has !Gez in its sign bit; with t = 2e - 3, Lqt <=> t^2 <= (8qt-5)^2,
     // so t*t + (2^31 - (8qt-5)^2 - 1) has !Lqt in bit 31.  Pixels are pushed from plane bit 15 down
     // to 0 (plane bit of pixel (x,y) is ((x^2)<<2)+y), so the accumulators ARE the planes.
-    if (kPixelPlanes) {
+    if (SEL == kSelPixels) {
         uint32_t accNeg = 0, accFar = 0;
 #pragma unroll
         for (int b = 15; b >= 0; --b) {
@@ -168,7 +262,11 @@ GB_DEV void encode_etc1(const uint32_t (&p)[16], const BlockFront& f, const uint
             accNeg = push_top_bit(accNeg, e);
             accFar = push_top_bit(accFar, t * t + f.cU);
         }
-        word1 = accNeg | (accFar << 16);
+        return accNeg | (accFar << 16);
+    } else if (SEL == kSelFlagBytes) {
+        uint32_t unused, planes;
+        selectors_from_flag_bytes<false, true>(p, f, unused, planes);
+        return planes;
     } else {
         // low lane walks columns 2,3 (plane bits 0..7), high lane columns 0,1 (plane bits 8..15)
         uint32_t accNeg = 0, accFar = 0;
@@ -181,9 +279,13 @@ GB_DEV void encode_etc1(const uint32_t (&p)[16], const BlockFront& f, const uint
             accFar = bitsel(~x2, accFar >> 1, 0x80008000u);  // !Lqt
         }
         // lanes hold their 8 flags at bits 7..14 (accNeg) and 8..15 (accFar)
-        word1 = prmt(accNeg >> 7, accFar >> 8, 0x6420);
+        return prmt(accNeg >> 7, accFar >> 8, 0x6420);
     }
+}
 
+// word0 of an ETC1s block: base colour 555 (in 888 positions) and the control byte
+GB_DEV uint32_t etc1_base_word(const uint32_t (&p)[16], const BlockFront& f, const uint32_t* controlLut)
+{
     // Average colour: the reference's fixed tree of rounded-UP averages (goofy_tc.h:1402-1414),
     // evaluated on complemented bytes so each node is a floor average (3 ops).
     uint32_t col[4];
@@ -206,7 +308,30 @@ GB_DEV void encode_etc1(const uint32_t (&p)[16], const BlockFront& f, const uint
     const uint32_t d2 = prmt((uint32_t)dm1, 0u, 0x1010);
     const uint32_t rb = addclamp_s16x2(avg & 0x00FF00FFu, d2, 0x00FE00FEu);   // lanes (R, B)
     const uint32_t g = (uint32_t)addclamp_s32((int)((avg >> 8) & 0xFFu), dm1, 254);
-    word0 = (rb & 0x00F800F8u) | ((g & 0xF8u) << 8) | controlLut[f.range];
+    return (rb & 0x00F800F8u) | ((g & 0xF8u) << 8) | controlLut[f.range];
+}
+
+template <int SEL = kSelPixels>
+GB_DEV void encode_etc1(const uint32_t (&p)[16], const BlockFront& f, const uint32_t* controlLut, uint32_t& word0,
+                        uint32_t& word1)
+{
+    word1 = etc1_planes<SEL>(p, f);
+    word0 = etc1_base_word(p, f, controlLut);
+}
+
+// Both codecs from one block: with the flag-byte scheme the twelve flag words are formed once and weighted twice.
+template <int SEL>
+GB_DEV void encode_both(const uint32_t (&p)[16], const BlockFront& f, const uint32_t* controlLut, uint32_t& dxt0,
+                        uint32_t& dxt1, uint32_t& etc0, uint32_t& etc1)
+{
+    if (SEL == kSelFlagBytes) {
+        selectors_from_flag_bytes<true, true>(p, f, dxt1, etc1);
+    } else {
+        dxt1 = dxt1_indices_lanes(p, f);
+        etc1 = etc1_planes<kSelLanes>(p, f);
+    }
+    dxt0 = dxt1_endpoints(f);
+    etc0 = etc1_base_word(p, f, controlLut);
 }
 
 // ======================================================================== float-reference flavour

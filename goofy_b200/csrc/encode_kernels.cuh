@@ -23,9 +23,38 @@ enum Mode : int { kDxt1 = 0, kEtc1 = 1, kDual = 2 };
 #ifndef GB_TPB
 #define GB_TPB 256     // threads per CTA of the direct / row-walking kernels (x a power of two, x*y == GB_TPB)
 #endif
-#ifndef GB_DUAL_CTAS
-#define GB_DUAL_CTAS 6   // resident CTAs per SM the dual-output kernels are compiled for (40 registers)
+// Resident 256-thread CTAs per SM each flavour is compiled for (8 -> 32 registers, 6 -> 40, 5 -> 48).
+#ifndef GB_CTAS_DXT1
+#define GB_CTAS_DXT1 8
 #endif
+#ifndef GB_CTAS_ETC1
+#define GB_CTAS_ETC1 6
+#endif
+#ifndef GB_CTAS_DUAL
+#define GB_CTAS_DUAL 6
+#endif
+// Row-walking kernels, bit mask by mode (1 DXT1, 2 ETC1s, 4 dual): prefetch the next block row of this thread into
+// L2 while the current one is encoded.  Measured SLOWER (ETC1s 5750 vs 6290 GB/s, dual 6450 vs 6550): kept as a knob.
+#ifndef GB_PREFETCH_L2
+#define GB_PREFETCH_L2 0
+#endif
+// Row-walking launches, bit mask by mode: use encode_rows_prefetch_kernel (register double buffer).
+#ifndef GB_REG_PREFETCH
+#define GB_REG_PREFETCH 0
+#endif
+
+// Selector-gathering scheme per kernel flavour (block_codec.cuh `Selectors`); -D overridable for A/B runs.
+#ifndef GB_SEL_DXT1
+#define GB_SEL_DXT1 kSelLanes
+#endif
+#ifndef GB_SEL_ETC1
+#define GB_SEL_ETC1 kSelFlagBytes
+#endif
+#ifndef GB_SEL_DUAL
+#define GB_SEL_DUAL kSelFlagBytes
+#endif
+
+constexpr int ctas_per_sm(int mode) { return mode == 0 ? GB_CTAS_DXT1 : mode == 1 ? GB_CTAS_ETC1 : GB_CTAS_DUAL; }
 
 struct EncodeParams {
     const uint8_t* src;
@@ -67,6 +96,8 @@ __device__ __forceinline__ uint4 load_row(const uint8_t* p)
     return v;
 }
 
+__device__ __forceinline__ void prefetch_l2(const uint8_t* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void store_block(uint8_t* p, uint32_t w0, uint32_t w1)
 {
 #ifndef GB_STORE_PTX
@@ -84,13 +115,17 @@ __device__ __forceinline__ void encode_and_store(const uint4& r0, const uint4& r
                             r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
     const BlockFront f = analyse(p);
     uint32_t w0, w1;
-    if (MODE == kDxt1 || MODE == kDual) {
-        encode_dxt1(p, f, w0, w1);
+    if (MODE == kDxt1) {
+        encode_dxt1<GB_SEL_DXT1>(p, f, w0, w1);
         store_block(dst, w0, w1);
-    }
-    if (MODE == kEtc1 || MODE == kDual) {
-        encode_etc1<MODE != kDual>(p, f, lut, w0, w1);
-        store_block(MODE == kDual ? dst2 : dst, w0, w1);
+    } else if (MODE == kEtc1) {
+        encode_etc1<GB_SEL_ETC1>(p, f, lut, w0, w1);
+        store_block(dst, w0, w1);
+    } else {
+        uint32_t e0, e1;
+        encode_both<GB_SEL_DUAL>(p, f, lut, w0, w1, e0, e1);
+        store_block(dst, w0, w1);
+        store_block(dst2, e0, e1);
     }
 }
 
@@ -101,7 +136,7 @@ __device__ __forceinline__ void encode_and_store(const uint4& r0, const uint4& r
 // PITCHED = true adds blockIdx.z * pitch for batches whose images are not back to back (batches
 // that ARE back to back are launched as one tall image, so the common case pays nothing).
 template <int MODE, bool WIDE, bool PITCHED>
-__global__ void __launch_bounds__(GB_TPB, (MODE == 2 ? GB_DUAL_CTAS : 8) * 256 / GB_TPB) encode_direct_kernel(const EncodeParams P)
+__global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) encode_direct_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     pdl_launch_dependents();
@@ -143,7 +178,7 @@ __global__ void __launch_bounds__(GB_TPB, (MODE == 2 ? GB_DUAL_CTAS : 8) * 256 /
 // (indices, control table, constants) is paid once and each further block costs only the
 // pointer bumps -- about 25 fewer instructions per block than one-shot CTAs.
 template <int MODE, bool WIDE>
-__global__ void __launch_bounds__(GB_TPB, (MODE == 2 ? GB_DUAL_CTAS : 8) * 256 / GB_TPB) encode_rows_kernel(const EncodeParams P)
+__global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) encode_rows_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     pdl_launch_dependents();
@@ -170,8 +205,73 @@ __global__ void __launch_bounds__(GB_TPB, (MODE == 2 ? GB_DUAL_CTAS : 8) * 256 /
         const uint4 r1 = load_row(P.src + o1);
         const uint4 r2 = load_row(P.src + o2);
         const uint4 r3 = load_row(P.src + o3);
+        if (GB_PREFETCH_L2 & (1 << MODE)) {
+            if (by + rowStep < P.bh) {
+                const off_t step = (off_t)rowStep * ((off_t)4u * P.stride);
+                prefetch_l2(P.src + o0 + step);
+                prefetch_l2(P.src + o1 + step);
+                prefetch_l2(P.src + o2 + step);
+                prefetch_l2(P.src + o3 + step);
+            }
+        }
         const off_t o = ((off_t)by * P.bw + bx) * 8u;
         encode_and_store<MODE>(r0, r1, r2, r3, lut, P.dst + o, MODE == kDual ? P.dst2 + o : nullptr);
+    }
+}
+
+// Row-walking CTAs with a REGISTER double buffer: the four row loads of a thread's next block are issued
+// before its current block is encoded, so every resident warp always has 2 KiB of loads in flight (the plain
+// row-walking kernel only has loads in flight while a warp waits, about half the time).  Costs 16 more
+// registers: GB_CTAS_PREFETCH CTAs per SM.  The loop is unrolled by two so the buffers swap roles without moves.
+#ifndef GB_CTAS_PREFETCH
+#define GB_CTAS_PREFETCH 4
+#endif
+template <int MODE, bool WIDE>
+__global__ void __launch_bounds__(GB_TPB, GB_CTAS_PREFETCH * 256 / GB_TPB) encode_rows_prefetch_kernel(const EncodeParams P)
+{
+    __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
+    pdl_launch_dependents();
+    pdl_wait();
+    if (MODE != kDxt1) {
+        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (uint32_t i = t; i < 256u; i += GB_TPB) lut[i] = g_etc1ControlLut[i];
+        __syncthreads();
+    }
+    const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t by = blockIdx.y * blockDim.y + threadIdx.y;
+    if (bx >= P.bw || by >= P.bh) return;
+
+    typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type off_t;
+    const uint32_t rowStep = gridDim.y * blockDim.y;
+    auto load4 = [&](uint32_t row, uint4& r0, uint4& r1, uint4& r2, uint4& r3) {
+        const off_t o0 = (off_t)row * ((off_t)4u * P.stride) + (off_t)(bx * 16u);
+        const off_t o1 = o0 + P.stride, o2 = o1 + P.stride, o3 = o2 + P.stride;
+        r0 = load_row(P.src + o0);
+        r1 = load_row(P.src + o1);
+        r2 = load_row(P.src + o2);
+        r3 = load_row(P.src + o3);
+    };
+    auto encode = [&](uint32_t row, const uint4& r0, const uint4& r1, const uint4& r2, const uint4& r3) {
+        const off_t o = ((off_t)row * P.bw + bx) * 8u;
+        encode_and_store<MODE>(r0, r1, r2, r3, lut, P.dst + o, MODE == kDual ? P.dst2 + o : nullptr);
+    };
+    uint4 a0, a1, a2, a3, b0, b1, b2, b3;
+    load4(by, a0, a1, a2, a3);
+#pragma unroll 1
+    for (;;) {
+        uint32_t byNext = by + rowStep;
+        bool more = byNext < P.bh;
+        if (more) load4(byNext, b0, b1, b2, b3);
+        encode(by, a0, a1, a2, a3);
+        if (!more) break;
+        by = byNext;
+        byNext = by + rowStep;
+        more = byNext < P.bh;
+        if (more) load4(byNext, a0, a1, a2, a3);
+        encode(by, b0, b1, b2, b3);
+        if (!more) break;
+        by = byNext;
     }
 }
 
@@ -299,7 +399,7 @@ __global__ void __launch_bounds__(256) encode_relaxed_kernel(const uint8_t* __re
     if (FLAVOUR == 0) {
         const BlockFront f = analyse(p);
         if (CODEC == kDxt1) encode_dxt1(p, f, w0, w1);
-        else encode_etc1<true>(p, f, lut, w0, w1);
+        else encode_etc1<kSelPixels>(p, f, lut, w0, w1);
     } else {
         const RefFront f = analyse_ref(p, CODEC == kDxt1 ? 32u : 64u);
         if (CODEC == kDxt1) encode_dxt1_ref(p, f, w0, w1);

@@ -7,6 +7,8 @@
 //   min3/max3   VIMNMX3.U16x2     3-input min/max on two u16 lanes
 //   min2/max2   VIMNMX.U16x2
 //   bitsel      LOP3.LUT          (a & m) | (b & ~m)
+//   sign_bytes  PRMT              byte permute in sign-replicate mode: four flag bytes (0x00 / 0xFF) from four sign bits
+//   dp4a_su     IDP.4A.S8.U8      4 x (s8*u8) + s32: subtracts the weights of the set flag bytes
 // These stand in for the SSE2 pminub/pmaxub/pavgb/punpck*/pmovmskb sequences of the
 // reference (GoofyTC/goofy_tc.h:170-396); the encoders do NOT transliterate those ops,
 // they use closed forms on u16x2 lanes.
@@ -55,6 +57,30 @@ GB_DEV uint32_t nor(uint32_t a, uint32_t b)
 }
 // per-lane clamp(a + b, 0, c) on one signed 32-bit value
 GB_DEV int addclamp_s32(int a, int b, int c) { return __viaddmin_s32_relu(a, b, c); }
+// Byte permute whose selector nibbles have bit 3 set: result byte = the MSB of the chosen byte of (a, b),
+// replicated over all 8 bits (0x00 or 0xFF).  kSel is the usual 4-nibble selector with 8 added to each nibble.
+template <uint32_t kSel>
+GB_DEV uint32_t sign_bytes(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "n"(kSel));
+    return r;
+}
+// c + sum of (signed byte of a) * (unsigned byte of w): with flag bytes 0x00 / 0xFF (= 0 / -1) this is
+// c minus the weights of the set flags.
+GB_DEV uint32_t dp4a_su(uint32_t a, uint32_t w, uint32_t c)
+{
+    int r;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(w), "r"((int)c));
+    return (uint32_t)r;
+}
+// c + sum of (unsigned byte of a) * (signed byte of w): pixel bytes against negative weights
+GB_DEV uint32_t dp4a_neg(uint32_t a, uint32_t w, uint32_t c)
+{
+    int r;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(w), "r"((int)c));
+    return (uint32_t)r;
+}
 
 #else  // host emulation (tests only)
 
@@ -103,6 +129,29 @@ GB_DEV int addclamp_s32(int a, int b, int c)
     int v = a + b;
     v = v > c ? c : v;
     return v < 0 ? 0 : v;
+}
+template <uint32_t kSel>
+GB_DEV uint32_t sign_bytes(uint32_t a, uint32_t b)
+{
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t s = (kSel >> (4 * i)) & 15u;
+        uint32_t byte = (uint32_t)(v >> (8 * (s & 7u))) & 255u;
+        if (s & 8u) byte = (byte & 0x80u) ? 0xFFu : 0u;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+GB_DEV uint32_t dp4a_su(uint32_t a, uint32_t w, uint32_t c)
+{
+    for (int i = 0; i < 4; ++i) c += (uint32_t)((int)(int8_t)(a >> (8 * i)) * (int)((w >> (8 * i)) & 255u));
+    return c;
+}
+GB_DEV uint32_t dp4a_neg(uint32_t a, uint32_t w, uint32_t c)
+{
+    for (int i = 0; i < 4; ++i) c += (uint32_t)((int)((a >> (8 * i)) & 255u) * (int)(int8_t)(w >> (8 * i)));
+    return c;
 }
 
 #endif

@@ -83,6 +83,19 @@ __global__ void __launch_bounds__(TPB) k_rows4v(const uint8_t* src, uint8_t* dst
     *(uint2*)(dst + ((size_t)by * bw + bx) * 8) = o;
 }
 
+// the dual-output kernel's pattern: 64 B read, two 8-byte blocks written to two output streams (4:1 read:write)
+__global__ void __launch_bounds__(256) k_rows4dual(const uint8_t* src, uint8_t* dst, uint8_t* dst2, uint32_t bw, uint32_t stride)
+{
+    const uint32_t bx = blockIdx.x * 256 + threadIdx.x, by = blockIdx.y;
+    const uint8_t* s = src + (size_t)by * 4 * stride + (size_t)bx * 16;
+    uint4 a = ldg_hint<0>(s), b = ldg_hint<0>(s + stride), c = ldg_hint<0>(s + 2 * (size_t)stride), d = ldg_hint<0>(s + 3 * (size_t)stride);
+    uint2 o, o2;
+    o.x = a.x ^ b.y ^ c.z ^ d.w; o.y = a.z ^ b.w ^ c.x ^ d.y;
+    o2.x = a.y ^ b.z ^ c.w ^ d.x; o2.y = a.w ^ b.x ^ c.y ^ d.z;
+    *(uint2*)(dst + ((size_t)by * bw + bx) * 8) = o;
+    *(uint2*)(dst2 + ((size_t)by * bw + bx) * 8) = o2;
+}
+
 // two vertically adjacent blocks per thread: 8 row loads in flight
 __global__ void __launch_bounds__(256) k_rows8(const uint8_t* src, uint8_t* dst, uint32_t bw, uint32_t stride)
 {
@@ -153,6 +166,7 @@ int main(int argc, char** argv)
     timeit("rows4/cs", (double)inBytes + outBytes, [&](int b) { k_rows4v<4, 256><<<dim3(bw / 256, bh), 256>>>(src[b], dst[b], bw, stride); });
     timeit("rows4/t128", (double)inBytes + outBytes, [&](int b) { k_rows4v<0, 128><<<dim3(bw / 128, bh), 128>>>(src[b], dst[b], bw, stride); });
     timeit("rows4/t512", (double)inBytes + outBytes, [&](int b) { k_rows4v<0, 512><<<dim3(bw / 512, bh), 512>>>(src[b], dst[b], bw, stride); });
+    timeit("rows4/dual", (double)inBytes + 2.0 * outBytes, [&](int b) { k_rows4dual<<<dim3(bw / 256, bh), 256>>>(src[b], dst[b], dst[b] + outBytes, bw, stride); });
     timeit("rows4x256", (double)inBytes + outBytes, [&](int b) { k_rows4x256<<<dim3(bw / 256, bh), 128>>>(src[b], dst[b], bw, stride); });
     timeit("rows8", (double)inBytes + outBytes, [&](int b) { k_rows8<<<dim3(bw / 256, bh / 2), 256>>>(src[b], dst[b], bw, stride); });
     timeit("readonly", (double)inBytes, [&](int b) { k_readonly<<<dim3(bw / 256, bh), 256>>>(src[b], (uint32_t*)dst[b], stride); });
