@@ -77,6 +77,7 @@ class ClockSampler:
         self.nvml = None
         self.handle = None
         self.sm_max = None
+        self._last = None
 
     def start(self):
         try:
@@ -97,22 +98,27 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._run_nvml if self.nvml else self._run_smi, daemon=True)
         self.thread.start()
 
-    def _sample_nvml(self):
+    def _sample_nvml(self, with_power=True):
         n = self.nvml
         try:
             sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-            pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
-            try:
-                rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-            except Exception:
-                rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-            self.samples.append((sm, pw, rs))
+            if with_power or self._last is None:
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self._last = (pw, rs)
+            self.samples.append((sm, self._last[0], self._last[1]))
         except Exception:
             pass
 
     def _run_nvml(self):
+        # SM clock every 2 ms; power and throttle reasons (slower queries on some drivers) every 8th sample
+        i = 0
         while not self.stop_flag.is_set():
-            self._sample_nvml()
+            self._sample_nvml(with_power=(i % 8 == 0))
+            i += 1
             time.sleep(0.002)
 
     def _run_smi(self):

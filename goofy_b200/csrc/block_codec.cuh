@@ -24,7 +24,6 @@ namespace gb {
 
 constexpr uint32_t kLuma = 0x00010201u;   // dp4a weights for bytes (R,G,B,A): R + 2G + B
 constexpr uint32_t kLuma2 = 0x00020402u;  // twice that
-constexpr uint32_t kLumaNeg = 0x00FFFEFFu;  // signed bytes (-1, -2, -1, 0): minus that
 
 // min / max of 16 words, two u16 lanes each, in 8 three-input ops
 template <bool kMax>
@@ -52,10 +51,10 @@ struct BlockFront {
     uint32_t mid;         // avg(minY, maxY)                      goofy_tc.h:1179
     uint32_t laneBias;    // dp4a accumulator that makes lane = (R+2G+B+3) - 4*mid + 0x4000
     uint32_t kLo, kHi;    // packed add constants: bit15 of (lane + kLo) <=> e >= 4 - 4qt, of (lane + kHi) <=> e >= 4qt
-    // flag-byte scheme: per-lane biases (both lanes) that put a threshold flag into bit 15 of Y4 = R+2G+B (+ bias) resp. bias - Y4
-    uint32_t fbG;         // Y4 + fbG : bit15 <=> e >= 0
-    uint32_t fbB;         // Y4 + fbB : bit15 <=> e >= 4qt
-    uint32_t fbNa;        // fbNa - Y4: bit15 <=> e < 4 - 4qt
+    // flag-byte scheme: lane = e + 0x8000 (bias fbG), whose bit 15 is G (e >= 0) as it stands
+    uint32_t fbG;         // lanes_of accumulator: R+2G+B + fbG = e + 0x8000 (one lane's worth)
+    uint32_t fbB;         // lane - fbB : bit15 <=> e >= 4qt       (both lanes)
+    uint32_t fbNa;        // fbNa - lane: bit15 <=> e < 4 - 4qt    (both lanes)
     // single-pixel form used by the ETC1s planes (everything on the multiply pipe):
     uint32_t cE;          // dp4a(pixel, kLuma,  cE) = e            -> bit31 <=> !Gez
     uint32_t cT;          // dp4a(pixel, kLuma2, cT) = t = 2e - 3
@@ -88,10 +87,10 @@ GB_DEV BlockFront analyse(const uint32_t (&p)[16])
     f.laneBias = 0x4003u - (f.mid << 2);
     f.kLo = (0x3FFCu + q4) * 0x10001u;
     f.kHi = (0x4000u - q4) * 0x10001u;
-    // e = Y4 + 3 - 4 mid; every biased lane stays inside 1..0xFFFE, so the two lanes never exchange a carry
-    f.fbG = (0x8003u - (f.mid << 2)) * 0x10001u;
-    f.fbB = (0x8003u - (f.mid << 2) - q4) * 0x10001u;
-    f.fbNa = (0x8000u + (f.mid << 2) - q4) * 0x10001u;
+    // e = R+2G+B + 3 - 4 mid; every biased lane stays inside 1..0xFFFE, so the two lanes never exchange a carry
+    f.fbG = 0x8003u - (f.mid << 2);
+    f.fbB = q4 * 0x10001u;
+    f.fbNa = (0x10003u - q4) * 0x10001u;   // (0x8000 + 3 - 4qt) - e, per lane
     f.cE = 3u - (f.mid << 2);
     f.cT = 2u * f.cE - 3u;
     const uint32_t a = 2u * q4 - 5u;   // 8qt - 5, 19..763
@@ -150,13 +149,10 @@ GB_DEV void selectors_from_flag_bytes(const uint32_t (&p)[16], const BlockFront&
         uint32_t b[2], na[2], g[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            // three biased copies of the pair's brightness lanes, each straight out of the multiply pipe
-            // (no separate adds): low lane = pixel x = 2h, high lane = pixel x = 2h + 1
-            const uint32_t lo = p[4 * y + 2 * h], hi = p[4 * y + 2 * h + 1];
-            const uint32_t t = dp4a(hi, kLuma, 0u);
-            g[h] = dp4a(lo, kLuma, t * 0x10000u + f.fbG);
-            b[h] = dp4a(lo, kLuma, t * 0x10000u + f.fbB);
-            na[h] = dp4a_neg(lo, kLumaNeg, t * 0xFFFF0000u + f.fbNa);
+            // low lane = pixel x = 2h, high lane = pixel x = 2h + 1; lane = e + 0x8000, so bit 15 is G as it stands
+            g[h] = lanes_of(p[4 * y + 2 * h], p[4 * y + 2 * h + 1], f.fbG);
+            b[h] = g[h] - f.fbB;
+            na[h] = f.fbNa - g[h];
         }
         const uint32_t outerL = sign_bytes<0xFDB9>(b[0], na[0]);
         const uint32_t outerR = sign_bytes<0xFDB9>(b[1], na[1]);
@@ -295,20 +291,22 @@ GB_DEV uint32_t etc1_base_word(const uint32_t (&p)[16], const BlockFront& f, con
         const uint32_t bot = floor_avg4_of_complements(p[8 + x], p[12 + x]);
         col[x] = floor_avg4(top, bot);
     }
-    const uint32_t avg = ~floor_avg4(floor_avg4(col[0], col[1]), floor_avg4(col[2], col[3]));
+    const uint32_t navg = floor_avg4(floor_avg4(col[0], col[1]), floor_avg4(col[2], col[3]));  // ~avg: bytes 255 - avg
 
     // Shift the average colour so its brightness becomes `mid` (goofy_tc.h:1431-1449):
     // base = clamp(avg + d, 0, 255) per channel with d = clamp(mid - Y(avg), -127, 127), then
     // to5(base) = (max(base,1) - 1) >> 3.  Both clamps fold into one: max(base,1) - 1 ==
     // clamp(avg + (d - 1), 0, 254), and "& 0xF8" leaves to5 << 3 in place.
-    const int avgY = (int)(dp4a(avg, kLuma, 3u) >> 2);
-    int dm1 = (int)f.mid - 1 - avgY;              // d - 1
+    // The tree leaves the COMPLEMENT of the average and it is used as it stands: R+2G+B of the complement is
+    // 1020 - Y4(avg), and (Y4 + 3) >> 2 == 255 - ((1020 - Y4) >> 2), so Y(avg) = 255 - (dp4a(navg) >> 2).
+    int dm1 = (int)f.mid - 256 + (int)(dp4a(navg, kLuma, 0u) >> 2);   // d - 1 = mid - 1 - Y(avg)
     dm1 = dm1 < -128 ? -128 : dm1;
     dm1 = dm1 > 126 ? 126 : dm1;
     const uint32_t d2 = prmt((uint32_t)dm1, 0u, 0x1010);
-    const uint32_t rb = addclamp_s16x2(avg & 0x00FF00FFu, d2, 0x00FE00FEu);   // lanes (R, B)
-    const uint32_t g = (uint32_t)addclamp_s32((int)((avg >> 8) & 0xFFu), dm1, 254);
-    return (rb & 0x00F800F8u) | ((g & 0xF8u) << 8) | controlLut[f.range];
+    const uint32_t rb = addclamp_s16x2(~navg & 0x00FF00FFu, d2, 0x00FE00FEu);   // lanes (R, B)
+    // green stays in bits 8..15: both addends are multiples of 256
+    const uint32_t g = (uint32_t)addclamp_s32((int)(~navg & 0x0000FF00u), dm1 * 256, 254 * 256);
+    return (rb & 0x00F800F8u) | (g & 0xF800u) | controlLut[f.range];
 }
 
 template <int SEL = kSelPixels>

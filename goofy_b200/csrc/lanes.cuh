@@ -74,13 +74,6 @@ GB_DEV uint32_t dp4a_su(uint32_t a, uint32_t w, uint32_t c)
     asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(w), "r"((int)c));
     return (uint32_t)r;
 }
-// c + sum of (unsigned byte of a) * (signed byte of w): pixel bytes against negative weights
-GB_DEV uint32_t dp4a_neg(uint32_t a, uint32_t w, uint32_t c)
-{
-    int r;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(w), "r"((int)c));
-    return (uint32_t)r;
-}
 
 #else  // host emulation (tests only)
 
@@ -146,11 +139,6 @@ GB_DEV uint32_t sign_bytes(uint32_t a, uint32_t b)
 GB_DEV uint32_t dp4a_su(uint32_t a, uint32_t w, uint32_t c)
 {
     for (int i = 0; i < 4; ++i) c += (uint32_t)((int)(int8_t)(a >> (8 * i)) * (int)((w >> (8 * i)) & 255u));
-    return c;
-}
-GB_DEV uint32_t dp4a_neg(uint32_t a, uint32_t w, uint32_t c)
-{
-    for (int i = 0; i < 4; ++i) c += (uint32_t)((int)((a >> (8 * i)) & 255u) * (int)(int8_t)(w >> (8 * i)));
     return c;
 }
 

@@ -110,10 +110,13 @@ if args.check:
 
 res = {name: {m: [] for m in ("dxt1", "etc1", "dual")} for name, _ in libs}
 for r in range(args.rounds):
+    # rotate the order every round: under a power cap the first build timed after a pause sees higher clocks
+    order = libs[r % len(libs):] + libs[:r % len(libs)]
     for mode in ("dxt1", "etc1", "dual"):
-        for name, lib in libs:
+        for name, lib in order:
             res[name][mode].append(timed(lib, mode, args.steps))
 for name, _ in libs:
-    print(f"{name:>12}: " + " | ".join(f"{m} " + "/".join(f"{v:.0f}" for v in res[name][m]) for m in ("dxt1", "etc1", "dual")) + "  GB/s")
+    print(f"{name:>12}: " + " | ".join(f"{m} " + "/".join(f"{v:.0f}" for v in res[name][m]) + f" (mean {sum(res[name][m]) / len(res[name][m]):.0f})"
+                                        for m in ("dxt1", "etc1", "dual")) + "  GB/s")
 if args.out:
     Path(args.out).write_text(json.dumps(res, indent=1))
