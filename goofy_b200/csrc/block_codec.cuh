@@ -279,18 +279,22 @@ GB_DEV uint32_t etc1_planes(const uint32_t (&p)[16], const BlockFront& f)
     }
 }
 
-// word0 of an ETC1s block: base colour 555 (in 888 positions) and the control byte
-GB_DEV uint32_t etc1_base_word(const uint32_t (&p)[16], const BlockFront& f, const uint32_t* controlLut)
+// Average colour: the reference's fixed tree of rounded-UP averages (goofy_tc.h:1402-1414), evaluated on
+// complemented bytes so each node is a floor average (3 ops).  First the part that reads the pixels: the four
+// column averages (complemented) -- after it the pixels are dead.
+GB_DEV void etc1_column_averages(const uint32_t (&p)[16], uint32_t (&col)[4])
 {
-    // Average colour: the reference's fixed tree of rounded-UP averages (goofy_tc.h:1402-1414),
-    // evaluated on complemented bytes so each node is a floor average (3 ops).
-    uint32_t col[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
         const uint32_t top = floor_avg4_of_complements(p[x], p[4 + x]);
         const uint32_t bot = floor_avg4_of_complements(p[8 + x], p[12 + x]);
         col[x] = floor_avg4(top, bot);
     }
+}
+
+// word0 of an ETC1s block from the column averages: base colour 555 (in 888 positions) and the control byte
+GB_DEV uint32_t etc1_base_word_from_columns(const uint32_t (&col)[4], uint32_t mid, uint32_t range, const uint32_t* controlLut)
+{
     const uint32_t navg = floor_avg4(floor_avg4(col[0], col[1]), floor_avg4(col[2], col[3]));  // ~avg: bytes 255 - avg
 
     // Shift the average colour so its brightness becomes `mid` (goofy_tc.h:1431-1449):
@@ -299,14 +303,21 @@ GB_DEV uint32_t etc1_base_word(const uint32_t (&p)[16], const BlockFront& f, con
     // clamp(avg + (d - 1), 0, 254), and "& 0xF8" leaves to5 << 3 in place.
     // The tree leaves the COMPLEMENT of the average and it is used as it stands: R+2G+B of the complement is
     // 1020 - Y4(avg), and (Y4 + 3) >> 2 == 255 - ((1020 - Y4) >> 2), so Y(avg) = 255 - (dp4a(navg) >> 2).
-    int dm1 = (int)f.mid - 256 + (int)(dp4a(navg, kLuma, 0u) >> 2);   // d - 1 = mid - 1 - Y(avg)
+    int dm1 = (int)mid - 256 + (int)(dp4a(navg, kLuma, 0u) >> 2);   // d - 1 = mid - 1 - Y(avg)
     dm1 = dm1 < -128 ? -128 : dm1;
     dm1 = dm1 > 126 ? 126 : dm1;
     const uint32_t d2 = prmt((uint32_t)dm1, 0u, 0x1010);
     const uint32_t rb = addclamp_s16x2(~navg & 0x00FF00FFu, d2, 0x00FE00FEu);   // lanes (R, B)
     // green stays in bits 8..15: both addends are multiples of 256
     const uint32_t g = (uint32_t)addclamp_s32((int)(~navg & 0x0000FF00u), dm1 * 256, 254 * 256);
-    return (rb & 0x00F800F8u) | (g & 0xF800u) | controlLut[f.range];
+    return (rb & 0x00F800F8u) | (g & 0xF800u) | controlLut[range];
+}
+
+GB_DEV uint32_t etc1_base_word(const uint32_t (&p)[16], const BlockFront& f, const uint32_t* controlLut)
+{
+    uint32_t col[4];
+    etc1_column_averages(p, col);
+    return etc1_base_word_from_columns(col, f.mid, f.range, controlLut);
 }
 
 template <int SEL = kSelPixels>

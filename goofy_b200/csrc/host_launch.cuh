@@ -67,6 +67,9 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     if (async)
         return narrow ? launch_encode(gb::encode_rows_async_kernel<MODE, false>, grid, block, stream, P)
                       : launch_encode(gb::encode_rows_async_kernel<MODE, true>, grid, block, stream, P);
+    if (((GB_PIPELINE) & (1 << MODE)) != 0)
+        return narrow ? launch_encode(gb::encode_rows_pipelined_kernel<MODE, false>, grid, block, stream, P)
+                      : launch_encode(gb::encode_rows_pipelined_kernel<MODE, true>, grid, block, stream, P);
     if (regPrefetch)
         return narrow ? launch_encode(gb::encode_rows_prefetch_kernel<MODE, false>, grid, block, stream, P)
                       : launch_encode(gb::encode_rows_prefetch_kernel<MODE, true>, grid, block, stream, P);
