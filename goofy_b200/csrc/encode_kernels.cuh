@@ -33,20 +33,6 @@ enum Mode : int { kDxt1 = 0, kEtc1 = 1, kDual = 2 };
 #ifndef GB_CTAS_DUAL
 #define GB_CTAS_DUAL 6
 #endif
-// Row-walking kernels, bit mask by mode (1 DXT1, 2 ETC1s, 4 dual): prefetch the next block row of this thread into
-// L2 while the current one is encoded.  Measured SLOWER (ETC1s 5750 vs 6290 GB/s, dual 6450 vs 6550): kept as a knob.
-#ifndef GB_PREFETCH_L2
-#define GB_PREFETCH_L2 0
-#endif
-// Row-walking launches, bit mask by mode: use encode_rows_pipelined_kernel (next loads issued mid-block).
-#ifndef GB_PIPELINE
-#define GB_PIPELINE 0
-#endif
-// Row-walking launches, bit mask by mode: use encode_rows_prefetch_kernel (register double buffer).
-#ifndef GB_REG_PREFETCH
-#define GB_REG_PREFETCH 0
-#endif
-
 // Selector-gathering scheme per kernel flavour (block_codec.cuh `Selectors`); -D overridable for A/B runs.
 #ifndef GB_SEL_DXT1
 #define GB_SEL_DXT1 kSelLanes
@@ -99,16 +85,6 @@ __device__ __forceinline__ uint4 load_row(const uint8_t* p)
                  : "l"(p));
     return v;
 }
-
-// Predicated form (no branch, so the load keeps its place in the instruction stream): v is left alone if !pred.
-__device__ __forceinline__ void load_row_if(uint4& v, const uint8_t* p, bool pred)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q " GB_LOAD_PTX " {%0,%1,%2,%3}, [%4];\n\t}"
-                 : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)
-                 : "l"(p), "r"((uint32_t)pred));
-}
-
-__device__ __forceinline__ void prefetch_l2(const uint8_t* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void store_block(uint8_t* p, uint32_t w0, uint32_t w1)
 {
@@ -217,135 +193,8 @@ __global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) enco
         const uint4 r1 = load_row(P.src + o1);
         const uint4 r2 = load_row(P.src + o2);
         const uint4 r3 = load_row(P.src + o3);
-        if (GB_PREFETCH_L2 & (1 << MODE)) {
-            if (by + rowStep < P.bh) {
-                const off_t step = (off_t)rowStep * ((off_t)4u * P.stride);
-                prefetch_l2(P.src + o0 + step);
-                prefetch_l2(P.src + o1 + step);
-                prefetch_l2(P.src + o2 + step);
-                prefetch_l2(P.src + o3 + step);
-            }
-        }
         const off_t o = ((off_t)by * P.bw + bx) * 8u;
         encode_and_store<MODE>(r0, r1, r2, r3, lut, P.dst + o, MODE == kDual ? P.dst2 + o : nullptr);
-    }
-}
-
-// Row-walking CTAs, software-pipelined WITHOUT extra registers: a block is encoded in two phases -- everything
-// that reads the pixels (bounding box, selector flags, the column averages of the ETC1s colour tree), then the
-// tail that does not (endpoint / base-colour packing, control table, stores).  The loads of the thread's NEXT
-// block are issued between the two, into the registers the pixels just vacated, so they are in flight during
-// the tail, the loop bookkeeping and the first wait of the next iteration.
-template <int MODE, bool WIDE>
-__global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) encode_rows_pipelined_kernel(const EncodeParams P)
-{
-    __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
-    pdl_launch_dependents();
-    pdl_wait();
-    if (MODE != kDxt1) {
-        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
-#pragma unroll
-        for (uint32_t i = t; i < 256u; i += GB_TPB) lut[i] = g_etc1ControlLut[i];
-        __syncthreads();
-    }
-    const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t by = blockIdx.y * blockDim.y + threadIdx.y;
-    if (bx >= P.bw || by >= P.bh) return;
-
-    typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type off_t;
-    const uint32_t rowStep = gridDim.y * blockDim.y;
-    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
-    auto load4 = [&](uint32_t row, bool pred) {
-        const off_t o0 = (off_t)row * ((off_t)4u * P.stride) + (off_t)(bx * 16u);
-        const off_t o1 = o0 + P.stride, o2 = o1 + P.stride, o3 = o2 + P.stride;
-        load_row_if(r0, P.src + o0, pred);
-        load_row_if(r1, P.src + o1, pred);
-        load_row_if(r2, P.src + o2, pred);
-        load_row_if(r3, P.src + o3, pred);
-    };
-    load4(by, true);
-#pragma unroll 1
-    for (;;) {
-        // ---- phase A: everything that reads the pixels
-        uint32_t dxtIdx = 0, etcPlanes = 0, col[4] = {0, 0, 0, 0};
-        BlockFront f;
-        {
-            const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
-                                    r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
-            f = analyse(p);
-            if (MODE == kDxt1) dxtIdx = GB_SEL_DXT1 == kSelFlagBytes ? (selectors_from_flag_bytes<true, false>(p, f, dxtIdx, etcPlanes), dxtIdx)
-                                                                     : dxt1_indices_lanes(p, f);
-            else if (MODE == kEtc1) etcPlanes = etc1_planes<GB_SEL_ETC1>(p, f);
-            else if (GB_SEL_DUAL == kSelFlagBytes) selectors_from_flag_bytes<true, true>(p, f, dxtIdx, etcPlanes);
-            else { dxtIdx = dxt1_indices_lanes(p, f); etcPlanes = etc1_planes<kSelLanes>(p, f); }
-            if (MODE != kDxt1) etc1_column_averages(p, col);
-        }
-        // ---- the next block's loads, into the vacated registers
-        const uint32_t byNext = by + rowStep;
-        const bool more = byNext < P.bh;
-        load4(byNext, more);
-        // ---- phase B: the tail
-        const off_t o = ((off_t)by * P.bw + bx) * 8u;
-        if (MODE == kDxt1 || MODE == kDual) store_block(P.dst + o, dxt1_endpoints(f), dxtIdx);
-        if (MODE != kDxt1) store_block((MODE == kDual ? P.dst2 : P.dst) + o, etc1_base_word_from_columns(col, f.mid, f.range, lut), etcPlanes);
-        if (!more) break;
-        by = byNext;
-    }
-}
-
-// Row-walking CTAs with a REGISTER double buffer: the four row loads of a thread's next block are issued
-// before its current block is encoded, so every resident warp always has 2 KiB of loads in flight (the plain
-// row-walking kernel only has loads in flight while a warp waits, about half the time).  Costs 16 more
-// registers: GB_CTAS_PREFETCH CTAs per SM.  The loop is unrolled by two so the buffers swap roles without moves.
-#ifndef GB_CTAS_PREFETCH
-#define GB_CTAS_PREFETCH 4
-#endif
-template <int MODE, bool WIDE>
-__global__ void __launch_bounds__(GB_TPB, GB_CTAS_PREFETCH * 256 / GB_TPB) encode_rows_prefetch_kernel(const EncodeParams P)
-{
-    __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
-    pdl_launch_dependents();
-    pdl_wait();
-    if (MODE != kDxt1) {
-        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
-#pragma unroll
-        for (uint32_t i = t; i < 256u; i += GB_TPB) lut[i] = g_etc1ControlLut[i];
-        __syncthreads();
-    }
-    const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t by = blockIdx.y * blockDim.y + threadIdx.y;
-    if (bx >= P.bw || by >= P.bh) return;
-
-    typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type off_t;
-    const uint32_t rowStep = gridDim.y * blockDim.y;
-    auto load4 = [&](uint32_t row, uint4& r0, uint4& r1, uint4& r2, uint4& r3) {
-        const off_t o0 = (off_t)row * ((off_t)4u * P.stride) + (off_t)(bx * 16u);
-        const off_t o1 = o0 + P.stride, o2 = o1 + P.stride, o3 = o2 + P.stride;
-        r0 = load_row(P.src + o0);
-        r1 = load_row(P.src + o1);
-        r2 = load_row(P.src + o2);
-        r3 = load_row(P.src + o3);
-    };
-    auto encode = [&](uint32_t row, const uint4& r0, const uint4& r1, const uint4& r2, const uint4& r3) {
-        const off_t o = ((off_t)row * P.bw + bx) * 8u;
-        encode_and_store<MODE>(r0, r1, r2, r3, lut, P.dst + o, MODE == kDual ? P.dst2 + o : nullptr);
-    };
-    uint4 a0, a1, a2, a3, b0, b1, b2, b3;
-    load4(by, a0, a1, a2, a3);
-#pragma unroll 1
-    for (;;) {
-        uint32_t byNext = by + rowStep;
-        bool more = byNext < P.bh;
-        if (more) load4(byNext, b0, b1, b2, b3);
-        encode(by, a0, a1, a2, a3);
-        if (!more) break;
-        by = byNext;
-        byNext = by + rowStep;
-        more = byNext < P.bh;
-        if (more) load4(byNext, a0, a1, a2, a3);
-        encode(by, b0, b1, b2, b3);
-        if (!more) break;
-        by = byNext;
     }
 }
 
@@ -472,8 +321,8 @@ __global__ void __launch_bounds__(256) encode_relaxed_kernel(const uint8_t* __re
     uint32_t w0, w1;
     if (FLAVOUR == 0) {
         const BlockFront f = analyse(p);
-        if (CODEC == kDxt1) encode_dxt1(p, f, w0, w1);
-        else encode_etc1<kSelPixels>(p, f, lut, w0, w1);
+        if (CODEC == kDxt1) encode_dxt1<GB_SEL_DXT1>(p, f, w0, w1);
+        else encode_etc1<GB_SEL_ETC1>(p, f, lut, w0, w1);
     } else {
         const RefFront f = analyse_ref(p, CODEC == kDxt1 ? 32u : 64u);
         if (CODEC == kDxt1) encode_dxt1_ref(p, f, w0, w1);

@@ -47,9 +47,8 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     const int sms = sm_count(dev);
     if (sms <= 0) return GOOFY_B200_E_DEVICE;
     const bool async = g_loadPath.load(std::memory_order_relaxed) == GOOFY_B200_LOAD_ASYNC;
-    constexpr bool regPrefetch = ((GB_REG_PREFETCH) & (1 << MODE)) != 0;
     const uint32_t resident = async ? (uint32_t)sms * (MODE == gb::kDual ? 5u : 6u)
-                                    : (uint32_t)sms * (uint32_t)(regPrefetch ? GB_CTAS_PREFETCH : gb::ctas_per_sm(MODE)) * (256u / (uint32_t)GB_TPB);
+                                    : (uint32_t)sms * (uint32_t)gb::ctas_per_sm(MODE) * (256u / (uint32_t)GB_TPB);
     // Each CTA walks a few block rows: enough to amortise the per-thread set-up, few enough that CTAs keep
     // retiring and restarting at staggered times (fully persistent CTAs run in lock-step and are 10 % slower;
     // profiles/r01_rows_grid_sweep.txt).  Never fewer CTAs than one resident wave.
@@ -67,12 +66,6 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     if (async)
         return narrow ? launch_encode(gb::encode_rows_async_kernel<MODE, false>, grid, block, stream, P)
                       : launch_encode(gb::encode_rows_async_kernel<MODE, true>, grid, block, stream, P);
-    if (((GB_PIPELINE) & (1 << MODE)) != 0)
-        return narrow ? launch_encode(gb::encode_rows_pipelined_kernel<MODE, false>, grid, block, stream, P)
-                      : launch_encode(gb::encode_rows_pipelined_kernel<MODE, true>, grid, block, stream, P);
-    if (regPrefetch)
-        return narrow ? launch_encode(gb::encode_rows_prefetch_kernel<MODE, false>, grid, block, stream, P)
-                      : launch_encode(gb::encode_rows_prefetch_kernel<MODE, true>, grid, block, stream, P);
     if (narrow) return launch_encode(gb::encode_rows_kernel<MODE, false>, grid, block, stream, P);
     return launch_encode(gb::encode_rows_kernel<MODE, true>, grid, block, stream, P);
 }
