@@ -229,14 +229,13 @@ int encode_host(int codec, void* result, const void* input, uint32_t width, uint
         return GOOFY_B200_OK;
     };
 
-    int slot = 0;
-    for (uint32_t r0 = 0; r0 < blockRows; r0 += stripRows, slot = (slot + 1) % kSlots) {
-        const uint32_t rows = blockRows - r0 < stripRows ? blockRows - r0 : stripRows;
+    // One strip: stage (if pageable) -> H2D -> kernel -> D2H, all on the slot's stream.
+    auto issue = [&](int slot, uint32_t r0, uint32_t rows) -> int {
         cudaStream_t s = t_pipe.stream[slot];
         const uint8_t* src = (const uint8_t*)input + (size_t)r0 * 4u * stride;
         if (stageIn || stageOut) {
-            rc = retire(slot);  // the staging strips of this slot are about to be reused
-            if (rc != GOOFY_B200_OK) return rc;
+            const int r = retire(slot);  // the staging strips of this slot are about to be reused
+            if (r != GOOFY_B200_OK) return r;
         }
         if (stageIn) {
             CopyPool::get().copy2d((uint8_t*)t_stage.in[slot], rowBytes, src, stride, rowBytes, (size_t)rows * 4u);
@@ -245,18 +244,32 @@ int encode_host(int codec, void* result, const void* input, uint32_t width, uint
             // stream order protects the slot's device scratch: its previous strip finished D2H on the same stream
             GB_CUDA(cudaMemcpy2DAsync(t_pipe.dIn[slot], rowBytes, src, stride, rowBytes, (size_t)rows * 4u, cudaMemcpyHostToDevice, s));
         }
-        rc = encode_any(codec, t_pipe.dOut[slot], t_pipe.dIn[slot], width, rows * 4u, (uint32_t)rowBytes, 0, 0, 1, s);
-        if (rc != GOOFY_B200_OK) return rc;
+        const int r = encode_any(codec, t_pipe.dOut[slot], t_pipe.dIn[slot], width, rows * 4u, (uint32_t)rowBytes, 0, 0, 1, s);
+        if (r != GOOFY_B200_OK) return r;
         GB_CUDA(cudaMemcpyAsync(stageOut ? t_stage.out[slot] : (void*)((uint8_t*)result + (size_t)r0 * outRowBytes), t_pipe.dOut[slot],
                                 (size_t)rows * outRowBytes, cudaMemcpyDeviceToHost, s));
         pending[slot].r0 = r0;
         pending[slot].rows = rows;
         pending[slot].live = true;
+        return GOOFY_B200_OK;
+    };
+    // On failure nothing may still be reading `input` or writing `result` when the caller gets control back.
+    auto fail = [&](int code) -> int {
+        for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(t_pipe.stream[i]);
+        cudaGetLastError();
+        return code;
+    };
+
+    int slot = 0;
+    for (uint32_t r0 = 0; r0 < blockRows; r0 += stripRows, slot = (slot + 1) % kSlots) {
+        const uint32_t rows = blockRows - r0 < stripRows ? blockRows - r0 : stripRows;
+        rc = issue(slot, r0, rows);
+        if (rc != GOOFY_B200_OK) return fail(rc);
     }
     // drain in strip order (the oldest outstanding strip is in the slot the loop would use next)
     for (int i = 0; i < kSlots; ++i, slot = (slot + 1) % kSlots) {
         rc = retire(slot);
-        if (rc != GOOFY_B200_OK) return rc;
+        if (rc != GOOFY_B200_OK) return fail(rc);
     }
     return GOOFY_B200_OK;
 }

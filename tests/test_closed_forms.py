@@ -91,3 +91,36 @@ def test_base_colour_correction_as_signed_clamp():
     ref = np.where(neg == 0, np.minimum(a + corr, 255), np.maximum(a - corr, 0))
     d = np.clip(mid - ay, -127, 127)
     assert np.array_equal(ref, np.clip(a + d, 0, 255))
+
+
+def test_flag_byte_lanes_and_weights():
+    """The flag-byte selector scheme (block_codec.cuh, selectors_from_flag_bytes): the three threshold flags are the
+    sign bits of u16 lanes that never exchange a carry, and the IDP weights rebuild the DXT1 index byte and the
+    ETC1s plane bytes from them -- for every brightness, mid and threshold that can occur."""
+    y4 = np.arange(0, 1021, dtype=np.int64).reshape(-1, 1, 1)      # R + 2G + B
+    mid = np.arange(0, 256, dtype=np.int64).reshape(1, -1, 1)
+    qt = np.arange(3, 97, dtype=np.int64).reshape(1, 1, -1)
+    q4 = 4 * qt
+    e = y4 + 3 - 4 * mid
+    g_lane = y4 + (0x8003 - 4 * mid) + 0 * q4                       # lanes_of(.., fbG)
+    b_lane = g_lane - q4                                            # g - fbB
+    na_lane = (0x10003 - q4) - g_lane                               # fbNa - g
+    for lane in (g_lane, b_lane, na_lane):                          # no borrow / carry between the two lanes of a word
+        assert lane.min() >= 1 and lane.max() <= 0xFFFE
+    G, B, NA = g_lane >> 15, b_lane >> 15, na_lane >> 15
+    assert np.array_equal(G.astype(bool), (e >= 0) + 0 * q4)
+    assert np.array_equal(B.astype(bool), e >= q4)
+    assert np.array_equal(NA.astype(bool), e < 4 - q4)
+    assert not np.any(NA & B) and not np.any(B & (1 - G))           # NA, B exclusive; B implies G
+    # the reference's flags in terms of the three
+    gez, lqt = e >= 0, (e >= 4 - q4) & (e < q4)
+    assert np.array_equal((1 - G).astype(bool), ~gez + (0 * q4).astype(bool)) and np.array_equal(1 - NA - B, lqt.astype(np.int64))
+    # DXT1: index = 2*Lqt + !Gez = 3 - (2 NA + 2 B + G): a row byte is 255 minus the weighted flags (weights 2*4^x and 4^x)
+    assert np.array_equal(2 * lqt + (1 - gez.astype(np.int64)), 3 - (2 * NA + 2 * B + G))
+    assert sum(3 * 4 ** x for x in range(4)) == 255
+    assert [2 * 4 ** x for x in range(4)] == [0x02, 0x08, 0x20, 0x80] and [4 ** x for x in range(4)] == [0x01, 0x04, 0x10, 0x40]
+    # ETC1s planes: pixel (x, y) sits at plane bit ((x^2)<<2)+y, i.e. byte (x<2), bit 4*(x&1)+y: weights 2^y and 2^(4+y)
+    for x in range(4):
+        for y in range(4):
+            bit = ((x ^ 2) << 2) + y
+            assert bit // 8 == (1 if x < 2 else 0) and bit % 8 == 4 * (x & 1) + y
