@@ -117,7 +117,7 @@ __device__ __forceinline__ void encode_and_store(const uint4& r0, const uint4& r
     }
 }
 
-// 8 resident CTAs per SM (32 registers) for the single-codec kernels, 6 for the dual-output one.
+// Resident CTAs per SM: 8 (32 registers) for DXT1, 6 (40 registers) for ETC1s and dual-output (ctas_per_sm).
 // WIDE = false: every byte offset inside one image fits 32 bits (the launcher checks), which
 // keeps the address arithmetic to a handful of 32-bit ops; WIDE = true is the same kernel with
 // 64-bit offsets for images of 4 GiB and more.
