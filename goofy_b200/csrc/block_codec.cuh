@@ -132,11 +132,12 @@ enum Selectors : int { kSelLanes = 0, kSelPixels = 1, kSelFlagBytes = 2 };
 #else
 #define GB_WEIGHT_TABLE static const
 #endif
-GB_WEIGHT_TABLE uint32_t kFlagWeights[15] = {
+GB_WEIGHT_TABLE uint32_t kFlagWeights[17] = {
     0x40100401u, 0x08020802u, 0x80208020u,                                  // DXT1: gez, outerL, outerR
     0x10011001u << 0, 0x10011001u << 1, 0x10011001u << 2, 0x10011001u << 3,  // ETC1 !Lqt plane, row y
     0x00001001u << 0, 0x00001001u << 1, 0x00001001u << 2, 0x00001001u << 3,  // ETC1 !Gez plane byte 1 (x = 0,1), row y
     0x10010000u << 0, 0x10010000u << 1, 0x10010000u << 2, 0x10010000u << 3,  // ETC1 !Gez plane byte 0 (x = 2,3), row y
+    0x10012002u, 0x10012002u << 2,   // ETC1-only kernel: !Gez flags of one pair from rows (y+1, y), y = 0 and y = 2
 };
 
 template <bool kDxt, bool kEtc>
@@ -144,6 +145,7 @@ GB_DEV void selectors_from_flag_bytes(const uint32_t (&p)[16], const BlockFront&
 {
     uint32_t idx = 0xFFu;
     uint32_t far0 = 0, far1 = 0, neg0 = 0xFFu, neg1 = 0xFFu;
+    uint32_t gAbove[2] = {0, 0};
 #pragma unroll
     for (int y = 3; y >= 0; --y) {
         uint32_t b[2], na[2], g[2];
@@ -156,6 +158,20 @@ GB_DEV void selectors_from_flag_bytes(const uint32_t (&p)[16], const BlockFront&
         }
         const uint32_t outerL = sign_bytes<0xFDB9>(b[0], na[0]);
         const uint32_t outerR = sign_bytes<0xFDB9>(b[1], na[1]);
+        if (kEtc && !kDxt) {
+            // ETC1s alone: a plane byte holds one PAIR column of all four rows, so the G flags are gathered per
+            // pair from two rows at a time -- bytes (G(2h,y+1), G(2h+1,y+1), G(2h,y), G(2h+1,y)) -- one IDP each
+            far1 = dp4a_su(outerL, kFlagWeights[3 + y], far1);
+            far0 = dp4a_su(outerR, kFlagWeights[3 + y], far0);
+            if (y & 1) {
+                gAbove[0] = g[0];
+                gAbove[1] = g[1];
+            } else {
+                neg1 = dp4a_su(sign_bytes<0xFDB9>(gAbove[0], g[0]), kFlagWeights[15 + (y >> 1)], neg1);
+                neg0 = dp4a_su(sign_bytes<0xFDB9>(gAbove[1], g[1]), kFlagWeights[15 + (y >> 1)], neg0);
+            }
+            continue;
+        }
         const uint32_t gez = sign_bytes<0xFDB9>(g[0], g[1]);
         if (kDxt) {
             if (y != 3) idx = idx * 256u + 0xFFu;
