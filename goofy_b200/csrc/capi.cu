@@ -195,7 +195,18 @@ int goofy_b200_block_sse_device(int codec, const void* d_blocks, const void* d_r
     P.bw = width / 4u;
     P.bh = height / 4u;
     P.stride = stride;
-    const dim3 grid((P.bw + 255u) / 256u, P.bh, 1);
+    // CTAs walk down the image: about one resident wave of them, and never more than kSseMaxBlocksPerThread
+    // block rows per thread (32-bit partial sums)
+    const uint32_t gx = (P.bw + 255u) / 256u;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    const int sms = sm_count(dev);
+    uint32_t gy = (uint32_t)(sms > 0 ? sms : 148) * 8u / gx;
+    const uint32_t gyMin = (P.bh + gb::kSseMaxBlocksPerThread - 1u) / gb::kSseMaxBlocksPerThread;
+    if (gy < gyMin) gy = gyMin;
+    if (gy < 1u) gy = 1u;
+    if (gy > P.bh) gy = P.bh;
+    const dim3 grid(gx, gy, 1);
     if (codec == GOOFY_B200_DXT1) gb::block_sse_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
     else gb::block_sse_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
     g_launches.fetch_add(1, std::memory_order_relaxed);

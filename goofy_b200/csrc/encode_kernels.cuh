@@ -332,9 +332,12 @@ __global__ void __launch_bounds__(256) encode_relaxed_kernel(const uint8_t* __re
 }
 
 // ------------------------------------------------------------------ ragged batches
-// Images of different shapes in one launch.  The host sorts nothing: it uploads the
-// descriptors plus an exclusive prefix sum of per-image CTA counts; each CTA finds its
-// image by binary search and its tile by one division.
+// Images of different shapes in one launch (mip chains, atlases).  The host sorts nothing: it provides the
+// descriptors plus an exclusive prefix sum of per-image CTA counts; each CTA finds its image by binary search
+// and its tile by one division.  A tile is 64 x 16 blocks, walked in four passes of 64 x 4 threads, so the
+// search and (ETC1s) the control-table staging are paid once per 1024 blocks.
+// Small batches (a mip chain is 10-14 images) travel as kernel parameters: the search then runs against the
+// constant bank instead of a chain of dependent global loads before the first pixel load can be issued.
 struct BatchImage {
     const uint8_t* src;
     uint8_t* dst;
@@ -343,12 +346,27 @@ struct BatchImage {
     uint32_t tilesX;  // CTAs per block row
 };
 
-constexpr int kBatchTileX = 64;  // blocks per CTA in x
-constexpr int kBatchTileY = 4;   // block rows per CTA
+constexpr int kBatchTileX = 64;    // blocks per CTA in x
+constexpr int kBatchTileY = 4;     // block rows per pass (threads in y)
+constexpr int kBatchPasses = 4;    // passes per CTA
+constexpr int kBatchInline = 48;   // largest batch passed as kernel parameters
 
-template <int MODE>
-__global__ void __launch_bounds__(kBatchTileX* kBatchTileY)
-    encode_batch_kernel(const BatchImage* __restrict__ images, const uint32_t* __restrict__ ctaStart, uint32_t nImages)
+struct BatchTableGlobal {
+    const BatchImage* images;
+    const uint32_t* ctaStart;
+    __device__ __forceinline__ uint32_t start(uint32_t i) const { return ctaStart[i]; }
+    __device__ __forceinline__ BatchImage image(uint32_t i) const { return images[i]; }
+};
+struct BatchTableInline {
+    BatchImage images[kBatchInline];
+    uint32_t ctaStart[kBatchInline];
+    __device__ __forceinline__ uint32_t start(uint32_t i) const { return ctaStart[i]; }
+    __device__ __forceinline__ BatchImage image(uint32_t i) const { return images[i]; }
+};
+
+template <int MODE, typename TABLE>
+__global__ void __launch_bounds__(kBatchTileX* kBatchTileY, ctas_per_sm(MODE))
+    encode_batch_kernel(const __grid_constant__ TABLE table, uint32_t nImages)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     if (MODE != kDxt1) {
@@ -356,25 +374,28 @@ __global__ void __launch_bounds__(kBatchTileX* kBatchTileY)
         lut[t] = g_etc1ControlLut[t];
         __syncthreads();
     }
-    // largest i with ctaStart[i] <= blockIdx.x
+    // largest i with start(i) <= blockIdx.x
     uint32_t lo = 0, hi = nImages;
     while (hi - lo > 1u) {
         const uint32_t m = (lo + hi) >> 1;
-        if (ctaStart[m] <= blockIdx.x) lo = m; else hi = m;
+        if (table.start(m) <= blockIdx.x) lo = m; else hi = m;
     }
-    const BatchImage im = images[lo];
-    const uint32_t local = blockIdx.x - ctaStart[lo];
+    const BatchImage im = table.image(lo);
+    const uint32_t local = blockIdx.x - table.start(lo);
     const uint32_t ty = local / im.tilesX, tx = local - ty * im.tilesX;
     const uint32_t bx = tx * kBatchTileX + threadIdx.x;
-    const uint32_t by = ty * kBatchTileY + threadIdx.y;
-    if (bx >= im.bw || by >= im.bh) return;
-
-    const uint8_t* s = im.src + (uint64_t)by * 4u * im.stride + (uint64_t)bx * 16u;
-    const uint4 r0 = load_row(s);
-    const uint4 r1 = load_row(s + im.stride);
-    const uint4 r2 = load_row(s + 2ull * im.stride);
-    const uint4 r3 = load_row(s + 3ull * im.stride);
-    encode_and_store<MODE>(r0, r1, r2, r3, lut, im.dst + ((uint64_t)by * im.bw + bx) * 8u, nullptr);
+    if (bx >= im.bw) return;
+#pragma unroll 1
+    for (uint32_t pass = 0; pass < (uint32_t)kBatchPasses; ++pass) {
+        const uint32_t by = (ty * kBatchPasses + pass) * kBatchTileY + threadIdx.y;
+        if (by >= im.bh) return;
+        const uint8_t* s = im.src + (uint64_t)by * 4u * im.stride + (uint64_t)bx * 16u;
+        const uint4 r0 = load_row(s);
+        const uint4 r1 = load_row(s + im.stride);
+        const uint4 r2 = load_row(s + 2ull * im.stride);
+        const uint4 r3 = load_row(s + 3ull * im.stride);
+        encode_and_store<MODE>(r0, r1, r2, r3, lut, im.dst + ((uint64_t)by * im.bw + bx) * 8u, nullptr);
+    }
 }
 
 }  // namespace gb

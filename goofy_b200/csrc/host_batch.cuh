@@ -6,10 +6,10 @@
 namespace {
 
 // ---------------------------------------------------------------- ragged batch
-template <int MODE>
-int launch_batch(const gb::BatchImage* dImages, const uint32_t* dStart, uint32_t n, uint32_t totalCtas, cudaStream_t stream)
+template <int MODE, typename TABLE>
+int launch_batch(const TABLE& table, uint32_t n, uint32_t totalCtas, cudaStream_t stream)
 {
-    gb::encode_batch_kernel<MODE><<<totalCtas, dim3(gb::kBatchTileX, gb::kBatchTileY, 1), 0, stream>>>(dImages, dStart, n);
+    gb::encode_batch_kernel<MODE, TABLE><<<totalCtas, dim3(gb::kBatchTileX, gb::kBatchTileY, 1), 0, stream>>>(table, n);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cuda_rc(cudaGetLastError());
 }
@@ -53,12 +53,21 @@ int encode_batch_current_device(int codec, const GoofyB200Image* descs, const ui
         im.stride = d.stride;
         im.tilesX = (im.bw + gb::kBatchTileX - 1u) / gb::kBatchTileX;
         start.push_back((uint32_t)total);
-        total += (uint64_t)im.tilesX * ((im.bh + gb::kBatchTileY - 1u) / gb::kBatchTileY);
+        total += (uint64_t)im.tilesX * ((im.bh + gb::kBatchTileY * gb::kBatchPasses - 1u) / (gb::kBatchTileY * gb::kBatchPasses));
         if (total > 0x7FFFFFFFull) return GOOFY_B200_E_ARGS;
         images.push_back(im);
     }
     if (images.empty()) return GOOFY_B200_OK;
     const uint32_t m = (uint32_t)images.size();
+    if (m <= (uint32_t)gb::kBatchInline) {
+        // small batch: descriptors and prefix sums go in as kernel parameters (no table upload, no arena)
+        gb::BatchTableInline T;
+        std::memset(&T, 0, sizeof(T));
+        std::memcpy(T.images, images.data(), (size_t)m * sizeof(gb::BatchImage));
+        std::memcpy(T.ctaStart, start.data(), (size_t)m * sizeof(uint32_t));
+        return codec == GOOFY_B200_DXT1 ? launch_batch<gb::kDxt1>(T, m, (uint32_t)total, stream)
+                                        : launch_batch<gb::kEtc1>(T, m, (uint32_t)total, stream);
+    }
     const size_t bytesImages = (size_t)m * sizeof(gb::BatchImage);
     const size_t bytes = bytesImages + (size_t)m * sizeof(uint32_t);
 
@@ -81,10 +90,11 @@ int encode_batch_current_device(int codec, const GoofyB200Image* descs, const ui
     std::memcpy(A.host, images.data(), bytesImages);
     std::memcpy((uint8_t*)A.host + bytesImages, start.data(), (size_t)m * sizeof(uint32_t));
     GB_CUDA(cudaMemcpyAsync(A.dev, A.host, bytes, cudaMemcpyHostToDevice, stream));
-    const gb::BatchImage* dImages = (const gb::BatchImage*)A.dev;
-    const uint32_t* dStart = (const uint32_t*)((const uint8_t*)A.dev + bytesImages);
-    rc = codec == GOOFY_B200_DXT1 ? launch_batch<gb::kDxt1>(dImages, dStart, m, (uint32_t)total, stream)
-                                  : launch_batch<gb::kEtc1>(dImages, dStart, m, (uint32_t)total, stream);
+    gb::BatchTableGlobal T;
+    T.images = (const gb::BatchImage*)A.dev;
+    T.ctaStart = (const uint32_t*)((const uint8_t*)A.dev + bytesImages);
+    rc = codec == GOOFY_B200_DXT1 ? launch_batch<gb::kDxt1>(T, m, (uint32_t)total, stream)
+                                  : launch_batch<gb::kEtc1>(T, m, (uint32_t)total, stream);
     if (rc != GOOFY_B200_OK) return rc;
     GB_CUDA(cudaEventRecord(A.done, stream));
     return GOOFY_B200_OK;

@@ -9,6 +9,7 @@
 //   bitsel      LOP3.LUT          (a & m) | (b & ~m)
 //   sign_bytes  PRMT              byte permute in sign-replicate mode: four flag bytes (0x00 / 0xFF) from four sign bits
 //   dp4a_su     IDP.4A.S8.U8      4 x (s8*u8) + s32: subtracts the weights of the set flag bytes
+//   absdiff_u8x4 VABSDIFF4.U8     |a - b| on four unsigned bytes
 // These stand in for the SSE2 pminub/pmaxub/pavgb/punpck*/pmovmskb sequences of the
 // reference (GoofyTC/goofy_tc.h:170-396); the encoders do NOT transliterate those ops,
 // they use closed forms on u16x2 lanes.
@@ -57,6 +58,8 @@ GB_DEV uint32_t nor(uint32_t a, uint32_t b)
 }
 // per-lane clamp(a + b, 0, c) on one signed 32-bit value
 GB_DEV int addclamp_s32(int a, int b, int c) { return __viaddmin_s32_relu(a, b, c); }
+// |a - b| per unsigned byte
+GB_DEV uint32_t absdiff_u8x4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
 // Byte permute whose selector nibbles have bit 3 set: result byte = the MSB of the chosen byte of (a, b),
 // replicated over all 8 bits (0x00 or 0xFF).  kSel is the usual 4-nibble selector with 8 added to each nibble.
 template <uint32_t kSel>
@@ -122,6 +125,15 @@ GB_DEV int addclamp_s32(int a, int b, int c)
     int v = a + b;
     v = v > c ? c : v;
     return v < 0 ? 0 : v;
+}
+GB_DEV uint32_t absdiff_u8x4(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const int x = (int)((a >> (8 * i)) & 255u), y = (int)((b >> (8 * i)) & 255u);
+        r |= (uint32_t)(x > y ? x - y : y - x) << (8 * i);
+    }
+    return r;
 }
 template <uint32_t kSel>
 GB_DEV uint32_t sign_bytes(uint32_t a, uint32_t b)

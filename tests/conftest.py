@@ -36,7 +36,7 @@ def kernel_math():
     build.mkdir(exist_ok=True)
     so = build / "libkernel_math_host.so"
     srcs = [ROOT / "tests" / "kernel_math_host.cpp", ROOT / "goofy_b200" / "csrc" / "block_codec.cuh",
-            ROOT / "goofy_b200" / "csrc" / "lanes.cuh"]
+            ROOT / "goofy_b200" / "csrc" / "block_decode.cuh", ROOT / "goofy_b200" / "csrc" / "lanes.cuh"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-x", "c++", "-fPIC", "-shared", "-o", str(so), str(srcs[0])],
                        check=True, capture_output=True)
@@ -53,6 +53,27 @@ def kernel_math():
         out = np.zeros(width * height // 2, dtype=np.uint8)
         rc = lib.kernel_math_compress(codec, out.ctypes.data_as(u8p), img.ctypes.data_as(u8p), width, height, stride)
         return rc, out
+
+    lib.kernel_math_decode.argtypes = [C.c_int, u8p, C.c_uint, C.c_uint, u8p]
+    lib.kernel_math_decode.restype = C.c_int
+    lib.kernel_math_sse.argtypes = [C.c_int, u8p, u8p, C.c_uint, C.c_uint, C.POINTER(C.c_ulonglong)]
+    lib.kernel_math_sse.restype = C.c_int
+
+    def decode(codec, blocks, width, height):
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
+        out = np.zeros((height, width, 4), dtype=np.uint8)
+        assert lib.kernel_math_decode(codec, blocks.ctypes.data_as(u8p), width, height, out.ctypes.data_as(u8p)) == 0
+        return out
+
+    def sse(codec, blocks, img, width, height):
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
+        img = np.ascontiguousarray(img, dtype=np.uint8).reshape(-1)
+        acc = (C.c_ulonglong * 3)()
+        assert lib.kernel_math_sse(codec, blocks.ctypes.data_as(u8p), img.ctypes.data_as(u8p), width, height, acc) == 0
+        return np.array([acc[0], acc[1], acc[2]], dtype=np.float64)
+
+    run.decode = decode
+    run.sse = sse
     return run
 
 

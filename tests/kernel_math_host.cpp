@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "../goofy_b200/csrc/block_codec.cuh"
+#include "../goofy_b200/csrc/block_decode.cuh"
 
 extern "C" int kernel_math_compress(int codec, unsigned char* result, const unsigned char* input, unsigned width,
                                     unsigned height, unsigned stride)
@@ -48,6 +49,39 @@ extern "C" int kernel_math_compress(int codec, unsigned char* result, const unsi
             std::memcpy(result, &w0, 4);
             std::memcpy(result + 4, &w1, 4);
             result += 8;
+        }
+    return 0;
+}
+
+// Decoders (block_decode.cuh): blocks -> RGBA8 image (tight stride), codec 0 = BC1, 1 = ETC1
+extern "C" int kernel_math_decode(int codec, const unsigned char* blocks, unsigned width, unsigned height, unsigned char* rgba)
+{
+    if (width % 4 || height % 4) return -1;
+    for (unsigned by = 0; by < height / 4; ++by)
+        for (unsigned bx = 0; bx < width / 4; ++bx) {
+            uint32_t w[2], px[16];
+            std::memcpy(w, blocks + ((size_t)by * (width / 4) + bx) * 8, 8);
+            if (codec == 0) gb::decode_block<0>(w[0], w[1], px);
+            else gb::decode_block<1>(w[0], w[1], px);
+            for (int y = 0; y < 4; ++y) std::memcpy(rgba + ((size_t)(4 * by + y) * width + 4 * bx) * 4, &px[4 * y], 16);
+        }
+    return 0;
+}
+
+// Fused decode + squared error against `rgba` (tight stride): sse[0..2] = R, G, B sums
+extern "C" int kernel_math_sse(int codec, const unsigned char* blocks, const unsigned char* rgba, unsigned width, unsigned height,
+                               unsigned long long* sse)
+{
+    if (width % 4 || height % 4) return -1;
+    sse[0] = sse[1] = sse[2] = 0;
+    for (unsigned by = 0; by < height / 4; ++by)
+        for (unsigned bx = 0; bx < width / 4; ++bx) {
+            uint32_t w[2], src[16], sr = 0, sg = 0, sb = 0;
+            std::memcpy(w, blocks + ((size_t)by * (width / 4) + bx) * 8, 8);
+            for (int y = 0; y < 4; ++y) std::memcpy(&src[4 * y], rgba + ((size_t)(4 * by + y) * width + 4 * bx) * 4, 16);
+            if (codec == 0) gb::block_sse<0>(w[0], w[1], src, sr, sg, sb);
+            else gb::block_sse<1>(w[0], w[1], src, sr, sg, sb);
+            sse[0] += sr; sse[1] += sg; sse[2] += sb;
         }
     return 0;
 }

@@ -124,3 +124,9 @@ def test_flag_byte_lanes_and_weights():
         for y in range(4):
             bit = ((x ^ 2) << 2) + y
             assert bit // 8 == (1 if x < 2 else 0) and bit % 8 == 4 * (x & 1) + y
+
+
+def test_third_by_multiply():
+    """floor(x / 3) == (x * 43691) >> 17 for every sum of three bytes (block_decode.cuh, BC1 thirds)."""
+    x = np.arange(0, 766, dtype=np.int64)
+    assert np.array_equal(x // 3, (x * 43691) >> 17)

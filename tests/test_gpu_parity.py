@@ -187,6 +187,38 @@ def test_ragged_batch_descriptors(codec, oracle):
 
 
 @pytest.mark.parametrize("codec", CODECS)
+def test_ragged_batch_large_table_and_tall_tiles(codec, oracle):
+    """More images than travel as kernel parameters (the descriptor table is uploaded instead), with heights on
+    both sides of the 16-block-row tile, plus a mip chain whose levels are sub-rectangles of one texture."""
+    rng = np.random.default_rng(5)
+    shapes = [(16 * int(rng.integers(1, 9)), 4 * int(rng.integers(1, 40))) for _ in range(60)] + [(1040, 68), (16, 260)]
+    imgs, dsts, descs, keep = [], [], [], []
+    for i, (w, h) in enumerate(shapes):
+        img = splitmix_rgba(w * h, seed=300 + i)
+        imgs.append(img)
+        keep.append(dev(img))
+        dsts.append(torch.zeros(w * h // 2, dtype=torch.uint8, device="cuda"))
+        descs.append((keep[-1], dsts[-1], w, h, w * 4))
+    assert gb.encode_batch_device(codec, descs) == 0
+    torch.cuda.synchronize()
+    for (w, h), img, d in zip(shapes, imgs, dsts):
+        assert np.array_equal(d.cpu().numpy(), oracle.compress(codec, img, w, h)[1]), (w, h)
+    # mip chain: level k is the top-left (size >> k)^2 corner of one 256x256 texture, pitch of the base level
+    base = synth_family(1, 256, 256, seed=3)
+    d_base = dev(base)
+    outs, chain, s = [], [], 256
+    while s >= 16:
+        outs.append(torch.zeros(s * s // 2, dtype=torch.uint8, device="cuda"))
+        chain.append((d_base, outs[-1], s, s, 256 * 4))
+        s //= 2
+    assert gb.encode_batch_device(codec, chain) == 0
+    torch.cuda.synchronize()
+    for (_, out, s, _, _) in chain:
+        want = oracle.compress(codec, np.ascontiguousarray(base.reshape(256, 256, 4)[:s, :s]), s, s)[1]
+        assert np.array_equal(out.cpu().numpy(), want), s
+
+
+@pytest.mark.parametrize("codec", CODECS)
 def test_sharded_host_equals_single(codec, oracle):
     w, h = 512, 200
     img = synth_family(1, w, h)

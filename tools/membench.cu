@@ -96,6 +96,19 @@ __global__ void __launch_bounds__(256) k_rows4dual(const uint8_t* src, uint8_t* 
     *(uint2*)(dst2 + ((size_t)by * bw + bx) * 8) = o2;
 }
 
+// the decoder's pattern, the encoder's mirrored: 8 bytes read, four 16-byte row stores (1:8 read:write)
+__global__ void __launch_bounds__(256) k_rows4decode(const uint8_t* blocks, uint8_t* rgba, uint32_t bw, uint32_t stride)
+{
+    const uint32_t bx = blockIdx.x * 256 + threadIdx.x, by = blockIdx.y;
+    const uint2 b = *(const uint2*)(blocks + ((size_t)by * bw + bx) * 8);
+    uint8_t* o = rgba + (size_t)by * 4 * stride + (size_t)bx * 16;
+    const uint4 v0 = make_uint4(b.x, b.y, b.x ^ b.y, ~b.x), v1 = make_uint4(b.y, b.x, ~b.y, b.x + b.y);
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(o), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w) : "memory");
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(o + stride), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(o + 2 * (size_t)stride), "r"(v0.y), "r"(v0.x), "r"(v0.w), "r"(v0.z) : "memory");
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(o + 3 * (size_t)stride), "r"(v1.y), "r"(v1.x), "r"(v1.w), "r"(v1.z) : "memory");
+}
+
 // two vertically adjacent blocks per thread: 8 row loads in flight
 __global__ void __launch_bounds__(256) k_rows8(const uint8_t* src, uint8_t* dst, uint32_t bw, uint32_t stride)
 {
@@ -167,6 +180,8 @@ int main(int argc, char** argv)
     timeit("rows4/t128", (double)inBytes + outBytes, [&](int b) { k_rows4v<0, 128><<<dim3(bw / 128, bh), 128>>>(src[b], dst[b], bw, stride); });
     timeit("rows4/t512", (double)inBytes + outBytes, [&](int b) { k_rows4v<0, 512><<<dim3(bw / 512, bh), 512>>>(src[b], dst[b], bw, stride); });
     timeit("rows4/dual", (double)inBytes + 2.0 * outBytes, [&](int b) { k_rows4dual<<<dim3(bw / 256, bh), 256>>>(src[b], dst[b], dst[b] + outBytes, bw, stride); });
+    timeit("rows4/decode", (double)inBytes + outBytes, [&](int b) { k_rows4decode<<<dim3(bw / 256, bh), 256>>>(dst[b], src[b], bw, stride); });
+    for (int i = 0; i < NBUF; ++i) cudaMemset(src[i], i + 1, inBytes);
     timeit("rows4x256", (double)inBytes + outBytes, [&](int b) { k_rows4x256<<<dim3(bw / 256, bh), 128>>>(src[b], dst[b], bw, stride); });
     timeit("rows8", (double)inBytes + outBytes, [&](int b) { k_rows8<<<dim3(bw / 256, bh / 2), 256>>>(src[b], dst[b], bw, stride); });
     timeit("readonly", (double)inBytes, [&](int b) { k_readonly<<<dim3(bw / 256, bh), 256>>>(src[b], (uint32_t*)dst[b], stride); });
