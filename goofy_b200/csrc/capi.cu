@@ -201,7 +201,8 @@ int goofy_b200_block_sse_device(int codec, const void* d_blocks, const void* d_r
     int dev = -1;
     cudaGetDevice(&dev);
     const int sms = sm_count(dev);
-    uint32_t gy = (uint32_t)(sms > 0 ? sms : 148) * 8u / gx;
+    static const uint32_t waves = []() { const char* e = getenv("GOOFY_B200_SSE_WAVES"); const int v = e ? atoi(e) : 1; return v > 0 ? (uint32_t)v : 1u; }();
+    uint32_t gy = (uint32_t)(sms > 0 ? sms : 148) * 8u * waves / gx;
     const uint32_t gyMin = (P.bh + gb::kSseMaxBlocksPerThread - 1u) / gb::kSseMaxBlocksPerThread;
     if (gy < gyMin) gy = gyMin;
     if (gy < 1u) gy = 1u;
