@@ -140,8 +140,11 @@ GB_WEIGHT_TABLE uint32_t kFlagWeights[17] = {
     0x10012002u, 0x10012002u << 2,   // ETC1-only kernel: !Gez flags of one pair from rows (y+1, y), y = 0 and y = 2
 };
 
-template <bool kDxt, bool kEtc>
-GB_DEV void selectors_from_flag_bytes(const uint32_t (&p)[16], const BlockFront& f, uint32_t& dxtWord1, uint32_t& etcWord1)
+// kWeights = dp4a weights of the brightness (kLuma for the SSE2-exact flavour, kLuma8 for the float-reference one);
+// fbG / fbB / fbNa = the three lane biases of that flavour (BlockFront / RefFront).
+template <bool kDxt, bool kEtc, uint32_t kWeights>
+GB_DEV void selectors_from_flag_bytes(const uint32_t (&p)[16], uint32_t fbG, uint32_t fbB, uint32_t fbNa, uint32_t& dxtWord1,
+                                      uint32_t& etcWord1)
 {
     uint32_t idx = 0xFFu;
     uint32_t far0 = 0, far1 = 0, neg0 = 0xFFu, neg1 = 0xFFu;
@@ -152,9 +155,10 @@ GB_DEV void selectors_from_flag_bytes(const uint32_t (&p)[16], const BlockFront&
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             // low lane = pixel x = 2h, high lane = pixel x = 2h + 1; lane = e + 0x8000, so bit 15 is G as it stands
-            g[h] = lanes_of(p[4 * y + 2 * h], p[4 * y + 2 * h + 1], f.fbG);
-            b[h] = g[h] - f.fbB;
-            na[h] = f.fbNa - g[h];
+            const uint32_t hi = dp4a(p[4 * y + 2 * h + 1], kWeights, fbG);
+            g[h] = dp4a(p[4 * y + 2 * h], kWeights, hi * 65536u + fbG);
+            b[h] = g[h] - fbB;
+            na[h] = fbNa - g[h];
         }
         const uint32_t outerL = sign_bytes<0xFDB9>(b[0], na[0]);
         const uint32_t outerR = sign_bytes<0xFDB9>(b[1], na[1]);
@@ -229,7 +233,7 @@ GB_DEV void encode_dxt1(const uint32_t (&p)[16], const BlockFront& f, uint32_t& 
 {
     if (SEL == kSelFlagBytes) {
         uint32_t unused;
-        selectors_from_flag_bytes<true, false>(p, f, word1, unused);
+        selectors_from_flag_bytes<true, false, kLuma>(p, f.fbG, f.fbB, f.fbNa, word1, unused);
     } else {
         word1 = dxt1_indices_lanes(p, f);
     }
@@ -277,7 +281,7 @@ GB_DEV uint32_t etc1_planes(const uint32_t (&p)[16], const BlockFront& f)
         return accNeg | (accFar << 16);
     } else if (SEL == kSelFlagBytes) {
         uint32_t unused, planes;
-        selectors_from_flag_bytes<false, true>(p, f, unused, planes);
+        selectors_from_flag_bytes<false, true, kLuma>(p, f.fbG, f.fbB, f.fbNa, unused, planes);
         return planes;
     } else {
         // low lane walks columns 2,3 (plane bits 0..7), high lane columns 0,1 (plane bits 8..15)
@@ -350,7 +354,7 @@ GB_DEV void encode_both(const uint32_t (&p)[16], const BlockFront& f, const uint
                         uint32_t& dxt1, uint32_t& etc0, uint32_t& etc1)
 {
     if (SEL == kSelFlagBytes) {
-        selectors_from_flag_bytes<true, true>(p, f, dxt1, etc1);
+        selectors_from_flag_bytes<true, true, kLuma>(p, f.fbG, f.fbB, f.fbNa, dxt1, etc1);
     } else {
         dxt1 = dxt1_indices_lanes(p, f);
         etc1 = etc1_planes<kSelLanes>(p, f);
@@ -373,7 +377,9 @@ constexpr uint32_t kLuma8 = 0x00081008u;  // dp4a weights 8R + 16G + 8B = 8 * Y4
 struct RefFront {
     uint32_t mnG, mxG, mnRB, mxRB;  // same layout as BlockFront
     uint32_t range4, mid8;
-    uint32_t laneBias, kLo, kHi;    // lane = d + 0x3FFF: bit 14 <=> d >= 1; bit 15 of (lane+kLo)^(lane+kHi) <=> |d| < Q
+    // flag-byte scheme (selectors_from_flag_bytes): lane = d + 0x7FFF, so bit 15 <=> d >= 1 ("diff > 0");
+    // bit 15 of (lane - fbB) <=> d >= Q; bit 15 of (fbNa - lane) <=> d <= -Q; near = neither of the last two
+    uint32_t fbG, fbB, fbNa;
 };
 
 GB_DEV RefFront analyse_ref(const uint32_t (&p)[16], uint32_t minRange4)
@@ -392,30 +398,18 @@ GB_DEV RefFront analyse_ref(const uint32_t (&p)[16], uint32_t minRange4)
     f.range4 = spread > minRange4 ? spread : minRange4;   // :549
     f.mid8 = maxY4 + minY4;                                // :551
     const uint32_t Q = 3u * f.range4;                      // :554
-    f.laneBias = 0x3FFFu - 4u * f.mid8;
-    f.kLo = (0x4000u + Q) * 0x10001u;
-    f.kHi = (0x4001u - Q) * 0x10001u;
+    // |d| <= 8160 and 96 <= Q <= 3060: every biased lane stays inside 1..0xFFFE
+    f.fbG = 0x7FFFu - 4u * f.mid8;
+    f.fbB = (Q - 1u) * 0x10001u;
+    f.fbNa = (0xFFFFu - Q) * 0x10001u;
     return f;
-}
-
-GB_DEV uint32_t ref_lanes_of(uint32_t a, uint32_t b, uint32_t laneBias)
-{
-    const uint32_t hi = dp4a(b, kLuma8, laneBias);
-    return dp4a(a, kLuma8, hi * 65536u + laneBias);
 }
 
 // :634-670  c0 = (R>>3)<<11 | (G>>3)<<6 | B>>3 | 0x20 from the max corner, c1 from the min corner
 GB_DEV void encode_dxt1_ref(const uint32_t (&p)[16], const RefFront& f, uint32_t& word0, uint32_t& word1)
 {
-    uint32_t acc = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint32_t e = ref_lanes_of(p[i], p[i + 8], f.laneBias);
-        const uint32_t x = (e + f.kLo) ^ (e + f.kHi);
-        const uint32_t z = bitsel(x, ~e, 0x80008000u);  // bit15 = near, bit14 = !(diff > 0)
-        acc = bitsel(z, acc >> 2, 0xC000C000u);
-    }
-    word1 = acc;
+    uint32_t unused;
+    selectors_from_flag_bytes<true, false, kLuma8>(p, f.fbG, f.fbB, f.fbNa, word1, unused);   // bit1 = near, bit0 = !(diff > 0)
     const uint32_t rr = prmt(f.mxRB, f.mnRB, 0x5010);
     const uint32_t bb = prmt(f.mxRB, f.mnRB, 0x7030);
     const uint32_t gg = prmt(f.mxG, f.mnG, 0x5410);
@@ -428,16 +422,8 @@ GB_DEV void encode_dxt1_ref(const uint32_t (&p)[16], const RefFront& f, uint32_t
 GB_DEV void encode_etc1_ref(const uint32_t (&p)[16], const RefFront& f, const uint32_t* controlLut, uint32_t& word0,
                             uint32_t& word1)
 {
-    uint32_t accNeg = 0, accFar = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int y = k & 3, x = k >> 2;
-        const uint32_t e = ref_lanes_of(p[4 * y + 2 + x], p[4 * y + x], f.laneBias);
-        const uint32_t x2 = (e + f.kLo) ^ (e + f.kHi);
-        accNeg = bitsel(~e, accNeg >> 1, 0x40004000u);
-        accFar = bitsel(~x2, accFar >> 1, 0x80008000u);
-    }
-    word1 = prmt(accNeg >> 7, accFar >> 8, 0x6420);
+    uint32_t unused;
+    selectors_from_flag_bytes<false, true, kLuma8>(p, f.fbG, f.fbB, f.fbNa, unused, word1);   // !(diff > 0) plane | far plane << 16
 
     uint32_t sumR = 0, sumG = 0, sumB = 0;  // :526-536 (avgColor * 16)
 #pragma unroll
