@@ -99,6 +99,21 @@ inline int encodeSharded(Codec codec, unsigned char* result, const unsigned char
     return goofy_b200_encode_sharded_host(codec, result, input, width, height, stride, nGpus);
 }
 
+// The step after the encoder (Src/main.cpp:561-613, :403-469): blocks -> RGBA8 on the device ...
+inline int decode(Codec codec, void* dRgba, const void* dBlocks, uint32_t width, uint32_t height, uint32_t stride,
+                  void* stream = nullptr)
+{
+    return goofy_b200_decode_device(codec, dRgba, dBlocks, width, height, stride, stream);
+}
+
+// ... and the per-channel sums of squared (decoded - source), ADDED to the three device uint64 at dSseRgb,
+// without writing the decoded image.  psnrRGB of the reference = 10 log10(768^2 / ((sse0+sse1+sse2) / pixels)).
+inline int blockSse(Codec codec, const void* dBlocks, const void* dRgba, uint32_t width, uint32_t height, uint32_t stride,
+                    uint64_t* dSseRgb, void* stream = nullptr)
+{
+    return goofy_b200_block_sse_device(codec, dBlocks, dRgba, width, height, stride, dSseRgb, stream);
+}
+
 }  // namespace b200
 }  // namespace goofy
 
