@@ -265,7 +265,7 @@ __device__ uint32_t g_etc1ControlLutRef[256];
 __global__ void fill_control_lut_ref_kernel() { g_etc1ControlLutRef[threadIdx.x] = etc1_control_word_ref(threadIdx.x); }
 
 template <int CODEC>
-__global__ void __launch_bounds__(256) encode_floatref_kernel(const EncodeParams P)
+__global__ void __launch_bounds__(256, 8) encode_floatref_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[CODEC == kDxt1 ? 1 : 256];
     if (CODEC != kDxt1) {
