@@ -23,7 +23,6 @@
 namespace gb {
 
 constexpr uint32_t kLuma = 0x00010201u;   // dp4a weights for bytes (R,G,B,A): R + 2G + B
-constexpr uint32_t kLuma2 = 0x00020402u;  // twice that
 
 // min / max of 16 words, two u16 lanes each, in 8 three-input ops
 template <bool kMax>
@@ -55,10 +54,6 @@ struct BlockFront {
     uint32_t fbG;         // lanes_of accumulator: R+2G+B + fbG = e + 0x8000 (one lane's worth)
     uint32_t fbB;         // lane - fbB : bit15 <=> e >= 4qt       (both lanes)
     uint32_t fbNa;        // fbNa - lane: bit15 <=> e < 4 - 4qt    (both lanes)
-    // single-pixel form used by the ETC1s planes (everything on the multiply pipe):
-    uint32_t cE;          // dp4a(pixel, kLuma,  cE) = e            -> bit31 <=> !Gez
-    uint32_t cT;          // dp4a(pixel, kLuma2, cT) = t = 2e - 3
-    uint32_t cU;          // t*t + cU                                -> bit31 <=> !Lqt   (Lqt <=> |2e-3| <= 8qt-5)
 };
 
 GB_DEV BlockFront analyse(const uint32_t (&p)[16])
@@ -91,10 +86,6 @@ GB_DEV BlockFront analyse(const uint32_t (&p)[16])
     f.fbG = 0x8003u - (f.mid << 2);
     f.fbB = q4 * 0x10001u;
     f.fbNa = (0x10003u - q4) * 0x10001u;   // (0x8000 + 3 - 4qt) - e, per lane
-    f.cE = 3u - (f.mid << 2);
-    f.cT = 2u * f.cE - 3u;
-    const uint32_t a = 2u * q4 - 5u;   // 8qt - 5, 19..763
-    f.cU = 0x7FFFFFFFu - a * a;        // 2^31 - ((8qt-5)^2 + 1)
     return f;
 }
 
@@ -108,13 +99,16 @@ GB_DEV uint32_t lanes_of(uint32_t a, uint32_t b, uint32_t laneBias)
 // bit15 of each lane <=> Lqt (|Y - mid| < qt)
 GB_DEV uint32_t lqt_lanes(uint32_t e, const BlockFront& f) { return (e + f.kLo) ^ (e + f.kHi); }
 
-// How the per-pixel flags (Gez, Lqt) are gathered into the output words.  All three give the same bits.
-//   kSelLanes      two pixels per register as biased u16 lanes, shift-and-insert accumulators (integer ALU pipe)
-//   kSelPixels     one pixel at a time on the multiply pipe, one funnel shift per flag (ETC1s planes only)
+// How the per-pixel flags (Gez, Lqt) are gathered into the output words.  Both give the same bits.
+//   kSelLanes      two pixels per register as biased u16 lanes, shift-and-insert accumulators on the integer ALU
+//                  pipe (DXT1 indices only; what the DRAM-bound DXT1 kernel uses)
 //   kSelFlagBytes  lanes as above, but the flags leave the lanes as 0x00 / 0xFF BYTES (one sign-replicating
 //                  PRMT per four flags) and are weighted into place by IDP.4A on the multiply pipe: 12 integer-ALU
-//                  instructions per block instead of 32-50, and the same twelve flag words feed both codecs.
-enum Selectors : int { kSelLanes = 0, kSelPixels = 1, kSelFlagBytes = 2 };
+//                  instructions per block instead of 32-50, and the same twelve flag words feed both codecs
+//                  (ETC1s, dual-output and float-reference kernels).
+// Two earlier ETC1s plane gatherers -- lanes with shift-and-insert accumulators, and one pixel at a time on the
+// multiply pipe with a funnel shift per flag -- were 16-20 % longer and are in the git history.
+enum Selectors : int { kSelLanes = 0, kSelFlagBytes = 2 };
 
 // Flag-byte scheme.  Per pixel three threshold flags, each the sign bit of a u16 lane (e = S - 4*mid):
 //   G  = e >= 0        NA = e < 4 - 4qt        B = e >= 4qt          (NA and B exclude each other; B implies G)
@@ -249,54 +243,11 @@ GB_DEV uint32_t floor_avg4_of_complements(uint32_t a, uint32_t b) { return nor(a
 // Output (goofy_tc.h:1358-1493): word0 = R5<<3 | G5<<11 | B5<<19 | control<<24;
 // word1 = ~(GezPlane | LqtPlane << 16), pixel (x,y) at plane bit ((x^2)<<2)+y.
 // `controlLut[range]` = control byte << 24 (the reference's table, goofy_tc.h:1040-1057).
-// SEL selects how the two selector planes are gathered (same result, see `Selectors`):
-//   kSelPixels  one pixel at a time on the multiply pipe (IDP/IMAD + 2 funnel shifts per pixel) -- relieves the
-//          integer ALU pipe, which is what bounds the ETC1s-only kernel (+1.6 % measured).  The compiler
-//          rewrites t*t - a*a as (t+a)*(t-a); forcing the single-IMAD form is 30 instructions shorter
-//          and 1.7 % SLOWER (6592 vs 6700 GB/s, A/B in one session), so it is left alone.  A variant that
-//          does the tests in FP32 with .SAT clamps (no integer ALU at all, exact, no spills, 277 instructions)
-//          was 3 % slower (6540 GB/s), and a one-IDP form, (e+4qt-3)*(4qt-e)-1, 16 instructions shorter,
-//          was 1 % slower (6710 GB/s): at ~0.76 instructions/clk/SMSP the kernel is issue-bound as well;
-//   kSelLanes   two pixels per register as biased u16 lanes (the DXT1 scheme) -- fewer instructions in total
-//          (dual-output kernel: 6478 vs 6068 GB/s measured).
-//   kSelFlagBytes  see selectors_from_flag_bytes.
-template <int SEL>
 GB_DEV uint32_t etc1_planes(const uint32_t (&p)[16], const BlockFront& f)
 {
-    // The two selector planes, one pixel at a time, entirely on the multiply pipe plus one funnel
-    // shift per flag: e = S - 4*mid has !Gez in its sign bit; with t = 2e - 3, Lqt <=> t^2 <= (8qt-5)^2,
-    // so t*t + (2^31 - (8qt-5)^2 - 1) has !Lqt in bit 31.  Pixels are pushed from plane bit 15 down
-    // to 0 (plane bit of pixel (x,y) is ((x^2)<<2)+y), so the accumulators ARE the planes.
-    if (SEL == kSelPixels) {
-        uint32_t accNeg = 0, accFar = 0;
-#pragma unroll
-        for (int b = 15; b >= 0; --b) {
-            const int x = (b >> 2) ^ 2, y = b & 3;
-            const uint32_t px = p[4 * y + x];
-            const uint32_t e = dp4a(px, kLuma, f.cE);
-            const uint32_t t = dp4a(px, kLuma2, f.cT);
-            accNeg = push_top_bit(accNeg, e);
-            accFar = push_top_bit(accFar, t * t + f.cU);
-        }
-        return accNeg | (accFar << 16);
-    } else if (SEL == kSelFlagBytes) {
-        uint32_t unused, planes;
-        selectors_from_flag_bytes<false, true, kLuma>(p, f.fbG, f.fbB, f.fbNa, unused, planes);
-        return planes;
-    } else {
-        // low lane walks columns 2,3 (plane bits 0..7), high lane columns 0,1 (plane bits 8..15)
-        uint32_t accNeg = 0, accFar = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int y = k & 3, x = k >> 2;
-            const uint32_t e = lanes_of(p[4 * y + 2 + x], p[4 * y + x], f.laneBias);
-            const uint32_t x2 = lqt_lanes(e, f);
-            accNeg = bitsel(~e, accNeg >> 1, 0x40004000u);   // !Gez
-            accFar = bitsel(~x2, accFar >> 1, 0x80008000u);  // !Lqt
-        }
-        // lanes hold their 8 flags at bits 7..14 (accNeg) and 8..15 (accFar)
-        return prmt(accNeg >> 7, accFar >> 8, 0x6420);
-    }
+    uint32_t unused, planes;
+    selectors_from_flag_bytes<false, true, kLuma>(p, f.fbG, f.fbB, f.fbNa, unused, planes);
+    return planes;
 }
 
 // Average colour: the reference's fixed tree of rounded-UP averages (goofy_tc.h:1402-1414), evaluated on
@@ -340,25 +291,18 @@ GB_DEV uint32_t etc1_base_word(const uint32_t (&p)[16], const BlockFront& f, con
     return etc1_base_word_from_columns(col, f.mid, f.range, controlLut);
 }
 
-template <int SEL = kSelPixels>
 GB_DEV void encode_etc1(const uint32_t (&p)[16], const BlockFront& f, const uint32_t* controlLut, uint32_t& word0,
                         uint32_t& word1)
 {
-    word1 = etc1_planes<SEL>(p, f);
+    word1 = etc1_planes(p, f);
     word0 = etc1_base_word(p, f, controlLut);
 }
 
-// Both codecs from one block: with the flag-byte scheme the twelve flag words are formed once and weighted twice.
-template <int SEL>
+// Both codecs from one block: the twelve flag words are formed once and weighted twice.
 GB_DEV void encode_both(const uint32_t (&p)[16], const BlockFront& f, const uint32_t* controlLut, uint32_t& dxt0,
                         uint32_t& dxt1, uint32_t& etc0, uint32_t& etc1)
 {
-    if (SEL == kSelFlagBytes) {
-        selectors_from_flag_bytes<true, true, kLuma>(p, f.fbG, f.fbB, f.fbNa, dxt1, etc1);
-    } else {
-        dxt1 = dxt1_indices_lanes(p, f);
-        etc1 = etc1_planes<kSelLanes>(p, f);
-    }
+    selectors_from_flag_bytes<true, true, kLuma>(p, f.fbG, f.fbB, f.fbNa, dxt1, etc1);
     dxt0 = dxt1_endpoints(f);
     etc0 = etc1_base_word(p, f, controlLut);
 }

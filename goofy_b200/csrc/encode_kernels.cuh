@@ -33,15 +33,10 @@ enum Mode : int { kDxt1 = 0, kEtc1 = 1, kDual = 2 };
 #ifndef GB_CTAS_DUAL
 #define GB_CTAS_DUAL 6
 #endif
-// Selector-gathering scheme per kernel flavour (block_codec.cuh `Selectors`); -D overridable for A/B runs.
+// Selector-gathering scheme of the DXT1 kernel (block_codec.cuh `Selectors`); -D overridable for A/B runs.
+// The ETC1s and dual-output kernels always use the flag-byte scheme.
 #ifndef GB_SEL_DXT1
 #define GB_SEL_DXT1 kSelLanes
-#endif
-#ifndef GB_SEL_ETC1
-#define GB_SEL_ETC1 kSelFlagBytes
-#endif
-#ifndef GB_SEL_DUAL
-#define GB_SEL_DUAL kSelFlagBytes
 #endif
 
 constexpr int ctas_per_sm(int mode) { return mode == 0 ? GB_CTAS_DXT1 : mode == 1 ? GB_CTAS_ETC1 : GB_CTAS_DUAL; }
@@ -107,11 +102,11 @@ __device__ __forceinline__ void encode_and_store(const uint4& r0, const uint4& r
         encode_dxt1<GB_SEL_DXT1>(p, f, w0, w1);
         store_block(dst, w0, w1);
     } else if (MODE == kEtc1) {
-        encode_etc1<GB_SEL_ETC1>(p, f, lut, w0, w1);
+        encode_etc1(p, f, lut, w0, w1);
         store_block(dst, w0, w1);
     } else {
         uint32_t e0, e1;
-        encode_both<GB_SEL_DUAL>(p, f, lut, w0, w1, e0, e1);
+        encode_both(p, f, lut, w0, w1, e0, e1);
         store_block(dst, w0, w1);
         store_block(dst2, e0, e1);
     }
@@ -322,7 +317,7 @@ __global__ void __launch_bounds__(256) encode_relaxed_kernel(const uint8_t* __re
     if (FLAVOUR == 0) {
         const BlockFront f = analyse(p);
         if (CODEC == kDxt1) encode_dxt1<GB_SEL_DXT1>(p, f, w0, w1);
-        else encode_etc1<GB_SEL_ETC1>(p, f, lut, w0, w1);
+        else encode_etc1(p, f, lut, w0, w1);
     } else {
         const RefFront f = analyse_ref(p, CODEC == kDxt1 ? 32u : 64u);
         if (CODEC == kDxt1) encode_dxt1_ref(p, f, w0, w1);

@@ -156,9 +156,6 @@ GB_DEV uint32_t dp4a_su(uint32_t a, uint32_t w, uint32_t c)
 
 #endif
 
-// (acc << 1) | (flagWord >> 31): one SHF (funnel shift) pulls the top bit of flagWord into the accumulator
-GB_DEV uint32_t push_top_bit(uint32_t acc, uint32_t flagWord) { return (acc << 1) | (flagWord >> 31); }
-
 // (a & m) | (b & ~m): one LOP3
 GB_DEV uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
 

@@ -13,9 +13,8 @@
 extern "C" int kernel_math_compress(int codec, unsigned char* result, const unsigned char* input, unsigned width,
                                     unsigned height, unsigned stride)
 {
-    const bool lanePlanes = (codec & 32) != 0;  // ETC1s: the two-pixels-per-register plane scheme
-    const bool flagBytes = (codec & 64) != 0;   // both codecs: the flag-byte scheme, through encode_both (dual-output kernel)
-    codec &= ~(32 | 64);
+    const bool fused = (codec & 64) != 0;   // through encode_both (the dual-output kernel), DXT1 with the flag-byte scheme
+    codec &= ~64;
     const bool floatRef = (codec & 16) != 0;   // GOOFY_B200_FLOATREF flavours (codec 16 / 17); goofyRef accepts width % 4
     codec &= 15;
     if (width % (floatRef ? 4 : 16)) return -1;
@@ -33,18 +32,17 @@ extern "C" int kernel_math_compress(int codec, unsigned char* result, const unsi
                 else gb::encode_etc1_ref(p, f, lut, w0, w1);
             } else {
                 const gb::BlockFront f = gb::analyse(p);
-                if (flagBytes) {
+                if (fused) {
                     uint32_t d0, d1, e0, e1, s0, s1;
-                    gb::encode_both<gb::kSelFlagBytes>(p, f, lut, d0, d1, e0, e1);
-                    // the single-codec entry points of the same scheme must agree with the fused one
+                    gb::encode_both(p, f, lut, d0, d1, e0, e1);
+                    // the single-codec entry points must agree with the fused one
                     if (codec == 0) gb::encode_dxt1<gb::kSelFlagBytes>(p, f, s0, s1);
-                    else gb::encode_etc1<gb::kSelFlagBytes>(p, f, lut, s0, s1);
+                    else gb::encode_etc1(p, f, lut, s0, s1);
                     w0 = codec == 0 ? d0 : e0;
                     w1 = codec == 0 ? d1 : e1;
                     if (s0 != w0 || s1 != w1) return -99;
                 } else if (codec == 0) gb::encode_dxt1<gb::kSelLanes>(p, f, w0, w1);
-                else if (lanePlanes) gb::encode_etc1<gb::kSelLanes>(p, f, lut, w0, w1);
-                else gb::encode_etc1<gb::kSelPixels>(p, f, lut, w0, w1);
+                else gb::encode_etc1(p, f, lut, w0, w1);
             }
             std::memcpy(result, &w0, 4);
             std::memcpy(result + 4, &w1, 4);

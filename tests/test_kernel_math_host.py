@@ -18,7 +18,7 @@ def test_kernel_math_on_fixtures(codec, kernel_math):
         h, w = img.shape[:2]
         rc, got = kernel_math(codec, img, w, h)
         assert rc == 0 and np.array_equal(got, fx[f"{n}_{KEY[codec]}"]), n
-        rc, got = kernel_math(codec | 64, img, w, h)   # flag-byte selector scheme (dual-output kernel)
+        rc, got = kernel_math(codec | 64, img, w, h)   # through the fused dual-output encoder
         assert rc == 0 and np.array_equal(got, fx[f"{n}_{KEY[codec]}"]), n
 
 
@@ -29,11 +29,8 @@ def test_kernel_math_on_synthetic(codec, family, kernel_math, oracle):
     want = oracle.compress(codec, img, 512, 512)[1]
     rc, got = kernel_math(codec, img, 512, 512)
     assert rc == 0 and np.array_equal(got, want)
-    rc, got = kernel_math(codec | 64, img, 512, 512)   # flag-byte selector scheme (dual-output kernel)
+    rc, got = kernel_math(codec | 64, img, 512, 512)   # through the fused dual-output encoder
     assert rc == 0 and np.array_equal(got, want)
-    if codec == ETC1:   # the two-pixels-per-register plane scheme
-        rc, got = kernel_math(codec | 32, img, 512, 512)
-        assert rc == 0 and np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("codec", CODECS)
@@ -49,8 +46,6 @@ def test_kernel_math_low_contrast_sweep(codec, kernel_math, oracle):
         assert rc == 0 and np.array_equal(got, oracle.compress(codec, img, 256, 256)[1]), spread
         rc2, got2 = kernel_math(codec | 64, img, 256, 256)
         assert rc2 == 0 and np.array_equal(got2, got), spread
-        if codec == ETC1:
-            assert np.array_equal(kernel_math(codec | 32, img, 256, 256)[1], got), spread
 
 
 @pytest.mark.parametrize("codec", CODECS)
@@ -107,8 +102,6 @@ def test_kernel_math_property_based(kernel_math, oracle):
             assert np.array_equal(kernel_math(codec, img, 16, 4)[1], want)
             rc, got = kernel_math(codec | 64, img, 16, 4)
             assert rc == 0 and np.array_equal(got, want)
-            if codec == ETC1:
-                assert np.array_equal(kernel_math(codec | 32, img, 16, 4)[1], want)
             assert np.array_equal(kernel_math(16 + codec, img, 16, 4)[1], oracle.compress_float_reference(codec, img, 16, 4)[1])
 
     run()
