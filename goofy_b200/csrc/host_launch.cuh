@@ -46,7 +46,11 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     const uint32_t rowGroups = (P.bh + ty - 1u) / ty;
     const int sms = sm_count(dev);
     if (sms <= 0) return GOOFY_B200_E_DEVICE;
-    const bool async = g_loadPath.load(std::memory_order_relaxed) == GOOFY_B200_LOAD_ASYNC;
+    // AUTO: the dual-output kernel walks its rows through the cp.async ring (next block in flight while the current one
+    // is encoded): +2-3 % over plain loads in every A/B session since it stopped being ALU-bound (r01f sessions 3, 8, 9);
+    // the single-codec kernels are faster with plain loads (ETC1s -5 % through the ring)
+    const int loadPath = g_loadPath.load(std::memory_order_relaxed);
+    const bool async = loadPath == GOOFY_B200_LOAD_ASYNC || (loadPath == GOOFY_B200_LOAD_AUTO && MODE == gb::kDual);
     const uint32_t resident = async ? (uint32_t)sms * (MODE == gb::kDual ? 5u : 6u)
                                     : (uint32_t)sms * (uint32_t)gb::ctas_per_sm(MODE) * (256u / (uint32_t)GB_TPB);
     // Each CTA walks a few block rows: enough to amortise the per-thread set-up, few enough that CTAs keep
@@ -80,8 +84,8 @@ int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream, int
         nImages = 1u;
     }
     // Load-path policy for AUTO: the DXT1 kernel is HBM-bound either way and
-    // one-shot CTAs are marginally faster (6617 vs 6598 GB/s); the ETC1s and dual-output kernels are
-    // instruction-bound and gain 4-13 % from row-walking CTAs.
+    // one-shot CTAs are marginally faster (6617 vs 6598 GB/s); the ETC1s and dual-output kernels
+    // gain 4-13 % from row-walking CTAs (dual-output: through the cp.async ring, see launch_rows).
     const int path = g_loadPath.load(std::memory_order_relaxed);
     const bool rows = path == GOOFY_B200_LOAD_DIRECT || path == GOOFY_B200_LOAD_ASYNC ||
                       (path == GOOFY_B200_LOAD_AUTO && MODE != gb::kDxt1);
