@@ -33,6 +33,11 @@ enum Mode : int { kDxt1 = 0, kEtc1 = 1, kDual = 2 };
 #ifndef GB_CTAS_DUAL
 #define GB_CTAS_DUAL 6
 #endif
+// Resident CTAs per SM of the cp.async ring kernels (33 KB of shared memory each)
+#ifndef GB_ASYNC_CTAS_DUAL
+#define GB_ASYNC_CTAS_DUAL 5
+#endif
+#define GB_ASYNC_CTAS(mode) ((mode) == 2 ? GB_ASYNC_CTAS_DUAL : 6)
 // Selector-gathering scheme of the DXT1 kernel (block_codec.cuh `Selectors`); -D overridable for A/B runs.
 // The ETC1s and dual-output kernels always use the flag-byte scheme.
 #ifndef GB_SEL_DXT1
@@ -207,7 +212,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int MODE, bool WIDE>
-__global__ void __launch_bounds__(GB_TPB, MODE == 2 ? 5 : 6) encode_rows_async_kernel(const EncodeParams P)
+__global__ void __launch_bounds__(GB_TPB, GB_ASYNC_CTAS(MODE)) encode_rows_async_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     __shared__ __align__(16) uint4 ring[2][4][GB_TPB];  // [stage][pixel row][thread]

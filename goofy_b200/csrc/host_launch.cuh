@@ -51,7 +51,7 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     // the single-codec kernels are faster with plain loads (ETC1s -5 % through the ring)
     const int loadPath = g_loadPath.load(std::memory_order_relaxed);
     const bool async = loadPath == GOOFY_B200_LOAD_ASYNC || (loadPath == GOOFY_B200_LOAD_AUTO && MODE == gb::kDual);
-    const uint32_t resident = async ? (uint32_t)sms * (MODE == gb::kDual ? 5u : 6u)
+    const uint32_t resident = async ? (uint32_t)sms * (uint32_t)GB_ASYNC_CTAS(MODE)
                                     : (uint32_t)sms * (uint32_t)gb::ctas_per_sm(MODE) * (256u / (uint32_t)GB_TPB);
     // Each CTA walks a few block rows: enough to amortise the per-thread set-up, few enough that CTAs keep
     // retiring and restarting at staggered times (fully persistent CTAs run in lock-step and are 10 % slower;
