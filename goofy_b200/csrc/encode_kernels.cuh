@@ -37,7 +37,10 @@ enum Mode : int { kDxt1 = 0, kEtc1 = 1, kDual = 2 };
 #ifndef GB_ASYNC_CTAS_DUAL
 #define GB_ASYNC_CTAS_DUAL 5
 #endif
-#define GB_ASYNC_CTAS(mode) ((mode) == 2 ? GB_ASYNC_CTAS_DUAL : 6)
+#ifndef GB_ASYNC_CTAS_SINGLE
+#define GB_ASYNC_CTAS_SINGLE 5
+#endif
+#define GB_ASYNC_CTAS(mode) ((mode) == 2 ? GB_ASYNC_CTAS_DUAL : GB_ASYNC_CTAS_SINGLE)
 // Selector-gathering scheme of the DXT1 kernel (block_codec.cuh `Selectors`); -D overridable for A/B runs.
 // The ETC1s and dual-output kernels always use the flag-byte scheme.
 #ifndef GB_SEL_DXT1
