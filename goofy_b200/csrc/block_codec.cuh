@@ -369,13 +369,15 @@ GB_DEV void encode_etc1_ref(const uint32_t (&p)[16], const RefFront& f, const ui
     uint32_t unused;
     selectors_from_flag_bytes<false, true, kLuma8>(p, f.fbG, f.fbB, f.fbNa, unused, word1);   // !(diff > 0) plane | far plane << 16
 
-    uint32_t sumR = 0, sumG = 0, sumB = 0;  // :526-536 (avgColor * 16)
+    // :526-536 (avgColor * 16).  Two channel sums per instruction: IDP.2A with the 16-bit weights (1, 4096) adds
+    // R + 4096 G (resp. B + 4096 A) of a pixel; sixteen bytes sum to at most 4080 < 4096, so the fields never meet.
+    uint32_t sumRG = 0, sumBA = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        sumR = dp4a(p[i], 0x00000001u, sumR);
-        sumG = dp4a(p[i], 0x00000100u, sumG);
-        sumB = dp4a(p[i], 0x00010000u, sumB);
+        sumRG = dp2a_lo(0x10000001u, p[i], sumRG);
+        sumBA = dp2a_hi(0x10000001u, p[i], sumBA);
     }
+    const uint32_t sumR = sumRG & 0xFFFu, sumG = sumRG >> 12, sumB = sumBA & 0xFFFu;
     // everything * 64: avg = sum * 4, avgY = sumR + 2 sumG + sumB, mid = mid8 * 8; floatToByte = floor(v + 0.5) clamped
     const int diffY64 = (int)(8u * f.mid8) - (int)(sumR + 2u * sumG + sumB);   // :606-607
     const int sums[3] = {(int)sumR, (int)sumG, (int)sumB};

@@ -10,6 +10,7 @@
 //   sign_bytes  PRMT              byte permute in sign-replicate mode: four flag bytes (0x00 / 0xFF) from four sign bits
 //   dp4a_su     IDP.4A.S8.U8      4 x (s8*u8) + s32: subtracts the weights of the set flag bytes
 //   absdiff_u8x4 VABSDIFF4.U8     |a - b| on four unsigned bytes
+//   dp2a_lo/hi  IDP.2A.LO/HI      2 x (u16*u8) + u32
 // These stand in for the SSE2 pminub/pmaxub/pavgb/punpck*/pmovmskb sequences of the
 // reference (GoofyTC/goofy_tc.h:170-396); the encoders do NOT transliterate those ops,
 // they use closed forms on u16x2 lanes.
@@ -60,6 +61,9 @@ GB_DEV uint32_t nor(uint32_t a, uint32_t b)
 GB_DEV int addclamp_s32(int a, int b, int c) { return __viaddmin_s32_relu(a, b, c); }
 // |a - b| per unsigned byte
 GB_DEV uint32_t absdiff_u8x4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
+// IDP.2A: c + w.lo16 * (byte 0 of px) + w.hi16 * (byte 1 of px)   resp. bytes 2 and 3
+GB_DEV uint32_t dp2a_lo(uint32_t w, uint32_t px, uint32_t c) { return __dp2a_lo(w, px, c); }
+GB_DEV uint32_t dp2a_hi(uint32_t w, uint32_t px, uint32_t c) { return __dp2a_hi(w, px, c); }
 // Byte permute whose selector nibbles have bit 3 set: result byte = the MSB of the chosen byte of (a, b),
 // replicated over all 8 bits (0x00 or 0xFF).  kSel is the usual 4-nibble selector with 8 added to each nibble.
 template <uint32_t kSel>
@@ -125,6 +129,14 @@ GB_DEV int addclamp_s32(int a, int b, int c)
     int v = a + b;
     v = v > c ? c : v;
     return v < 0 ? 0 : v;
+}
+GB_DEV uint32_t dp2a_lo(uint32_t w, uint32_t px, uint32_t c)
+{
+    return c + (w & 0xFFFFu) * (px & 255u) + (w >> 16) * ((px >> 8) & 255u);
+}
+GB_DEV uint32_t dp2a_hi(uint32_t w, uint32_t px, uint32_t c)
+{
+    return c + (w & 0xFFFFu) * ((px >> 16) & 255u) + (w >> 16) * (px >> 24);
 }
 GB_DEV uint32_t absdiff_u8x4(uint32_t a, uint32_t b)
 {
