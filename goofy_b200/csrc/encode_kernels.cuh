@@ -296,11 +296,12 @@ __global__ void __launch_bounds__(256, 8) encode_floatref_kernel(const EncodePar
 
 // Relaxed shapes: any width / height >= 1 and any 4-byte-aligned stride.  Blocks that
 // hang over the right or bottom edge replicate the last column / row (clamp-to-edge), so the output has
-// ceil(w/4) x ceil(h/4) blocks.  Sixteen clamped 32-bit loads per thread instead of four 128-bit ones: this
-// is the convenience path for odd-sized mip levels, not the roofline path.  FLAVOUR 0 = SSE2-exact
-// arithmetic, 1 = float-reference arithmetic; on images the strict entry points accept, the bytes are the same.
+// ceil(w/4) x ceil(h/4) blocks.  Blocks that lie wholly inside the image take the four 128-bit row loads of the
+// strict kernels when the rows are 16-byte aligned (a uniform condition); edge blocks and unaligned images take
+// sixteen clamped 32-bit loads.  FLAVOUR 0 = SSE2-exact arithmetic, 1 = float-reference arithmetic; on images the
+// strict entry points accept, the bytes are the same.
 template <int CODEC, int FLAVOUR>
-__global__ void __launch_bounds__(256) encode_relaxed_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+__global__ void __launch_bounds__(256, 6) encode_relaxed_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                              uint32_t width, uint32_t height, uint32_t stride)
 {
     __shared__ uint32_t lut[CODEC == kDxt1 ? 1 : 256];
@@ -312,13 +313,23 @@ __global__ void __launch_bounds__(256) encode_relaxed_kernel(const uint8_t* __re
     const uint32_t bx = blockIdx.x * 256u + threadIdx.x, by = blockIdx.y;
     if (bx >= bw || by >= bh) return;
     uint32_t p[16];
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | stride) & 15u) == 0u;
+    if (aligned && bx * 4u + 3u < width && by * 4u + 3u < height) {
+        const uint8_t* s = src + (uint64_t)by * 4u * stride + (uint64_t)bx * 16u;
+        const uint4 r0 = load_row(s), r1 = load_row(s + stride), r2 = load_row(s + 2ull * stride), r3 = load_row(s + 3ull * stride);
+        p[0] = r0.x; p[1] = r0.y; p[2] = r0.z; p[3] = r0.w;
+        p[4] = r1.x; p[5] = r1.y; p[6] = r1.z; p[7] = r1.w;
+        p[8] = r2.x; p[9] = r2.y; p[10] = r2.z; p[11] = r2.w;
+        p[12] = r3.x; p[13] = r3.y; p[14] = r3.z; p[15] = r3.w;
+    } else {
 #pragma unroll
-    for (int y = 0; y < 4; ++y) {
-        const uint32_t row = min(by * 4u + (uint32_t)y, height - 1u);
+        for (int y = 0; y < 4; ++y) {
+            const uint32_t row = min(by * 4u + (uint32_t)y, height - 1u);
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            const uint32_t col = min(bx * 4u + (uint32_t)x, width - 1u);
-            p[4 * y + x] = __ldg(reinterpret_cast<const uint32_t*>(src + (uint64_t)row * stride + (uint64_t)col * 4u));
+            for (int x = 0; x < 4; ++x) {
+                const uint32_t col = min(bx * 4u + (uint32_t)x, width - 1u);
+                p[4 * y + x] = __ldg(reinterpret_cast<const uint32_t*>(src + (uint64_t)row * stride + (uint64_t)col * 4u));
+            }
         }
     }
     uint32_t w0, w1;
