@@ -168,6 +168,41 @@ def test_uniform_batch_and_dual(codec, oracle):
             assert np.array_equal(d_b[i].cpu().numpy(), oracle.compress(ETC1, imgs[i], w, h)[1])
 
 
+@pytest.mark.parametrize("shape", [(16, 4), (272, 12), (1040, 68), (4112, 36), (64, 1028)])
+def test_dual_output_shapes_strides_and_pitches(shape, oracle):
+    """Both codecs from one read (AUTO: row-walking CTAs through the cp.async ring; pitched batches: one-shot CTAs):
+    ragged widths and heights, a padded stride whose pad bytes must be ignored, and images that are not back to back."""
+    w, h = shape
+    stride = w * 4 + 48
+    n = 3
+    pitch = stride * h + 256           # not back to back -> the pitched one-shot launch
+    out_pitch = w * h // 2 + 64
+    rng = np.random.default_rng(w + h)
+    host = rng.integers(0, 256, size=n * pitch, dtype=np.uint8)
+    imgs = []
+    for i in range(n):
+        rows = host[i * pitch: i * pitch + stride * h].reshape(h, stride)
+        imgs.append(np.ascontiguousarray(rows[:, : w * 4]).reshape(-1))
+    d_src = dev(host)
+    d_a = torch.zeros(n * out_pitch, dtype=torch.uint8, device="cuda")
+    d_b = torch.zeros(n * out_pitch, dtype=torch.uint8, device="cuda")
+    assert gb.encode_dual_device(d_a, d_b, d_src, w, h, stride, pitch, out_pitch, n) == 0
+    # the first image alone: a single (tall, if h is large) image through the AUTO row-walking launch
+    d_a1 = torch.zeros(w * h // 2, dtype=torch.uint8, device="cuda")
+    d_b1 = torch.zeros(w * h // 2, dtype=torch.uint8, device="cuda")
+    assert gb.encode_dual_device(d_a1, d_b1, d_src, w, h, stride) == 0
+    torch.cuda.synchronize()
+    a, b = d_a.cpu().numpy(), d_b.cpu().numpy()
+    for i in range(n):
+        want_d = oracle.compress(DXT1, imgs[i], w, h)[1]
+        want_e = oracle.compress(ETC1, imgs[i], w, h)[1]
+        assert np.array_equal(a[i * out_pitch: i * out_pitch + w * h // 2], want_d), (shape, i)
+        assert np.array_equal(b[i * out_pitch: i * out_pitch + w * h // 2], want_e), (shape, i)
+        assert not a[i * out_pitch + w * h // 2: (i + 1) * out_pitch].any()      # gaps between results untouched
+    assert np.array_equal(d_a1.cpu().numpy(), oracle.compress(DXT1, imgs[0], w, h)[1])
+    assert np.array_equal(d_b1.cpu().numpy(), oracle.compress(ETC1, imgs[0], w, h)[1])
+
+
 @pytest.mark.parametrize("codec", CODECS)
 def test_ragged_batch_descriptors(codec, oracle):
     shapes = [(16, 4), (64, 64), (272, 12), (1024, 8), (48, 100), (0, 0), (320, 36)]
