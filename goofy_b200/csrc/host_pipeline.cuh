@@ -2,6 +2,7 @@
 // three streams; pageable buffers staged through pinned strips by a small pool of copy threads.
 #pragma once
 #include "host_launch.cuh"
+#include "copy_pool.h"
 
 namespace {
 
@@ -66,90 +67,6 @@ struct HostPipe {
 
 thread_local HostPipe t_pipe;
 
-// Pageable (malloc'd) host buffers cannot be DMA'd directly; the CUDA driver then stages them through
-// one small internal buffer at ~10 GB/s.  The library stages them itself instead: a few persistent host
-// threads copy each strip into pinned memory in parallel while the previous strips are in flight.
-class CopyPool {
-public:
-    static CopyPool& get()
-    {
-        static CopyPool* pool = new CopyPool();  // leaked on purpose (see HostPipe)
-        return *pool;
-    }
-    // dst/src rows of `rowBytes`, `rows` of them; the calling thread takes a share of the rows too
-    void copy2d(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t rows)
-    {
-        if (rows * rowBytes < (1u << 20) || workers_.empty()) {
-            run(dst, dstPitch, src, srcPitch, rowBytes, 0, rows);
-            return;
-        }
-        std::lock_guard<std::mutex> serial(jobMutex_);  // one copy job at a time
-        {
-            std::lock_guard<std::mutex> g(m_);
-            dst_ = dst; dstPitch_ = dstPitch; src_ = src; srcPitch_ = srcPitch; rowBytes_ = rowBytes; rows_ = rows;
-            pending_ = (int)workers_.size();
-            ++generation_;
-        }
-        cv_.notify_all();
-        const size_t parts = workers_.size() + 1;
-        run(dst, dstPitch, src, srcPitch, rowBytes, rows * (parts - 1) / parts, rows);  // the caller's share: the last slice
-        std::unique_lock<std::mutex> g(m_);
-        done_.wait(g, [this] { return pending_ == 0; });
-    }
-
-    void copy1d(uint8_t* dst, const uint8_t* src, size_t bytes)
-    {
-        const size_t chunk = 1u << 16, full = bytes / chunk;
-        if (full) copy2d(dst, chunk, src, chunk, chunk, full);
-        if (bytes > full * chunk) std::memcpy(dst + full * chunk, src + full * chunk, bytes - full * chunk);
-    }
-
-private:
-    CopyPool()
-    {
-        unsigned n = std::thread::hardware_concurrency();
-        n = n > 16u ? 7u : (n > 2u ? n / 2u - 1u : 0u);  // plus the calling thread
-        for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this, i] { loop(i); });
-        for (auto& t : workers_) t.detach();
-    }
-    static void run(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t r0, size_t r1)
-    {
-        if (dstPitch == rowBytes && srcPitch == rowBytes) {
-            std::memcpy(dst + r0 * rowBytes, src + r0 * rowBytes, (r1 - r0) * rowBytes);
-            return;
-        }
-        for (size_t r = r0; r < r1; ++r) std::memcpy(dst + r * dstPitch, src + r * srcPitch, rowBytes);
-    }
-    void loop(unsigned index)
-    {
-        uint64_t seen = 0;
-        for (;;) {
-            uint8_t* dst; const uint8_t* src; size_t dp, sp, rb, rows;
-            {
-                std::unique_lock<std::mutex> g(m_);
-                cv_.wait(g, [&] { return generation_ != seen; });
-                seen = generation_;
-                dst = dst_; src = src_; dp = dstPitch_; sp = srcPitch_; rb = rowBytes_; rows = rows_;
-            }
-            const size_t parts = workers_.size() + 1;
-            run(dst, dp, src, sp, rb, rows * index / parts, rows * (index + 1) / parts);
-            {
-                std::lock_guard<std::mutex> g(m_);
-                --pending_;
-            }
-            done_.notify_one();
-        }
-    }
-    std::vector<std::thread> workers_;
-    std::mutex jobMutex_, m_;
-    std::condition_variable cv_, done_;
-    uint8_t* dst_ = nullptr;
-    const uint8_t* src_ = nullptr;
-    size_t dstPitch_ = 0, srcPitch_ = 0, rowBytes_ = 0, rows_ = 0;
-    int pending_ = 0;
-    uint64_t generation_ = 0;
-};
-
 // Pinned staging strips, allocated only when a pageable buffer is first seen by this thread.
 struct HostStage {
     void* in[kSlots] = {};
@@ -204,7 +121,20 @@ int encode_host(int codec, void* result, const void* input, uint32_t width, uint
 
     const size_t rowBytes = (size_t)width * 4u;
     const uint32_t blockRows = height / 4u;
-    uint32_t stripRows = (uint32_t)(kStripBytes / (rowBytes * 4u));
+    // Strips of whole block rows: about eight per image so that staging, H2D, kernel and D2H of neighbouring strips
+    // overlap even for images of a few megabytes, between 2 MiB (below that the per-strip fixed costs dominate: a
+    // 768x512 image took 74 us in three strips against 52 us in one) and kStripBytes (the scratch a host thread keeps
+    // per slot; 16 MiB and 8 MiB strips measure the same on 8192^2, 4 MiB and 2 MiB are 30-40 % slower for pageable buffers).
+    const size_t totalIn = rowBytes * (size_t)height;
+    size_t stripTarget = totalIn / 8u;
+    if (stripTarget < (2u << 20)) stripTarget = 2u << 20;
+    static const size_t stripCap = []() -> size_t {   // GOOFY_B200_STRIP_MB: experiments only (1..16)
+        const char* e = getenv("GOOFY_B200_STRIP_MB");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 1 && v <= 16) ? (size_t)v << 20 : kStripBytes;
+    }();
+    if (stripTarget > stripCap) stripTarget = stripCap;
+    uint32_t stripRows = (uint32_t)(stripTarget / (rowBytes * 4u));
     if (stripRows == 0u) stripRows = 1u;
     if (stripRows > blockRows) stripRows = blockRows;
     const size_t outRowBytes = (size_t)(width / 4u) * 8u;

@@ -1,0 +1,36 @@
+"""Host-side logic of the library that needs no GPU: the copy pool behind the drop-in host path."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+SRC = ROOT / "tests" / "copy_pool_stress.cpp"
+BUILD = ROOT / "tests" / "_build"
+
+
+def _build(flags, name):
+    BUILD.mkdir(exist_ok=True)
+    exe = BUILD / name
+    res = subprocess.run(["g++", "-std=c++17", "-pthread", *flags, "-o", str(exe), str(SRC)], capture_output=True, text=True)
+    return exe if res.returncode == 0 else None
+
+
+def test_copy_pool_stress():
+    """Spin-then-sleep wake-up handshake of CopyPool (goofy_b200/csrc/copy_pool.h): every copy of 2000 jobs of
+    varying size is checked, with pauses that let the workers fall asleep between jobs."""
+    exe = _build(["-O2"], "copy_pool_stress")
+    assert exe is not None
+    out = subprocess.run([str(exe), "2000"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
+def test_copy_pool_under_thread_sanitizer():
+    exe = _build(["-O1", "-g", "-fsanitize=thread"], "copy_pool_stress_tsan")
+    if exe is None:
+        pytest.skip("toolchain without ThreadSanitizer")
+    out = subprocess.run([str(exe), "400"], capture_output=True, text=True, timeout=240)
+    if "FATAL: ThreadSanitizer" in out.stderr and "unexpected memory mapping" in out.stderr:
+        pytest.skip("ThreadSanitizer cannot run in this container (ASLR layout)")
+    assert out.returncode == 0 and "WARNING: ThreadSanitizer" not in out.stderr, out.stderr[-2000:]
+    assert out.stdout.startswith("ok")
