@@ -136,6 +136,16 @@ def encode_host(codec: int, result, input, width: int, height: int, stride: int)
                                                   width, height, stride))
 
 
+def encode_host_batch(codec: int, images) -> int:
+    """images: iterable of (input, result, width, height, stride) with HOST buffers (numpy uint8 arrays or pinned
+    torch tensors).  One pipeline for all of them: copies and kernels of neighbouring images overlap."""
+    items = list(images)
+    arr = (GoofyB200Image * max(len(items), 1))()
+    for i, (src, dst, w, h, stride) in enumerate(items):
+        arr[i] = GoofyB200Image(_host_ptr(src, False), _host_ptr(dst, True), w, h, stride, -1)
+    return int(_lib.load().goofy_b200_encode_host_batch(codec, arr, len(items)))
+
+
 def encode_sharded_host(codec: int, result, input, width: int, height: int, stride: int, n_gpus: int = 0) -> int:
     """One host image, horizontal strips of whole block rows, strip g on GPU g (no collectives)."""
     return int(_lib.load().goofy_b200_encode_sharded_host(codec, _host_ptr(result, True), _host_ptr(input, False),

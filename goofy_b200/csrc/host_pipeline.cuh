@@ -107,24 +107,21 @@ bool is_pageable(const void* p)
     return a.type == cudaMemoryTypeUnregistered;
 }
 
-int encode_host(int codec, void* result, const void* input, uint32_t width, uint32_t height, uint32_t stride)
-{
-    if (!is_codec(codec)) return GOOFY_B200_E_CODEC;
-    int rc = is_floatref(codec) ? check_shape_floatref(width, height, stride) : check_shape(width, height, stride);
-    if (rc != GOOFY_B200_OK) return rc;
-    if (width == 0u || height == 0u) return GOOFY_B200_OK;
-    if (!result || !input) return GOOFY_B200_E_NULL;
-    if (((uintptr_t)input & 15u) != 0u) return GOOFY_B200_E_ALIGN;  // the reference's aligned-load contract
-    int dev = -1;
-    rc = ensure_device_ready(&dev);
-    if (rc != GOOFY_B200_OK) return rc;
+// One host image of a host-pointer call, validated and cut into strips.
+struct HostJob {
+    const uint8_t* input = nullptr;
+    uint8_t* result = nullptr;
+    uint32_t width = 0, stride = 0, blockRows = 0, stripRows = 0;
+    size_t rowBytes = 0, outRowBytes = 0;
+    bool stageIn = false, stageOut = false;
+};
 
-    const size_t rowBytes = (size_t)width * 4u;
-    const uint32_t blockRows = height / 4u;
-    // Strips of whole block rows: about eight per image so that staging, H2D, kernel and D2H of neighbouring strips
-    // overlap even for images of a few megabytes, between 2 MiB (below that the per-strip fixed costs dominate: a
-    // 768x512 image took 74 us in three strips against 52 us in one) and kStripBytes (the scratch a host thread keeps
-    // per slot; 16 MiB and 8 MiB strips measure the same on 8192^2, 4 MiB and 2 MiB are 30-40 % slower for pageable buffers).
+// Strips of whole block rows: about eight per image so that staging, H2D, kernel and D2H of neighbouring strips
+// overlap even for images of a few megabytes, between 2 MiB (below that the per-strip fixed costs dominate: a
+// 768x512 image took 74 us in three strips against 52 us in one) and kStripBytes (the scratch a host thread keeps
+// per slot; 16 MiB and 8 MiB strips measure the same on 8192^2, 4 MiB and 2 MiB are 30-40 % slower for pageable buffers).
+uint32_t strip_rows_for(size_t rowBytes, uint32_t height)
+{
     const size_t totalIn = rowBytes * (size_t)height;
     size_t stripTarget = totalIn / 8u;
     if (stripTarget < (2u << 20)) stripTarget = 2u << 20;
@@ -136,54 +133,93 @@ int encode_host(int codec, void* result, const void* input, uint32_t width, uint
     if (stripTarget > stripCap) stripTarget = stripCap;
     uint32_t stripRows = (uint32_t)(stripTarget / (rowBytes * 4u));
     if (stripRows == 0u) stripRows = 1u;
-    if (stripRows > blockRows) stripRows = blockRows;
-    const size_t outRowBytes = (size_t)(width / 4u) * 8u;
-    const size_t stripIn = (size_t)stripRows * 4u * rowBytes, stripOut = (size_t)stripRows * outRowBytes;
-    rc = t_pipe.prepare(dev, stripIn, stripOut);
-    if (rc != GOOFY_B200_OK) return rc;
+    const uint32_t blockRows = height / 4u;
+    return stripRows > blockRows ? blockRows : stripRows;
+}
 
+// The argument checks of one host image, in the reference's order (goofy_tc.h:1500-1508) and then the new ones.
+// Returns GOOFY_B200_OK with job.blockRows == 0 for an empty image.
+int make_host_job(int codec, void* result, const void* input, uint32_t width, uint32_t height, uint32_t stride, HostJob& job)
+{
+    int rc = is_floatref(codec) ? check_shape_floatref(width, height, stride) : check_shape(width, height, stride);
+    if (rc != GOOFY_B200_OK) return rc;
+    job = HostJob();
+    if (width == 0u || height == 0u) return GOOFY_B200_OK;
+    if (!result || !input) return GOOFY_B200_E_NULL;
+    if (((uintptr_t)input & 15u) != 0u) return GOOFY_B200_E_ALIGN;  // the reference's aligned-load contract
+    job.input = (const uint8_t*)input;
+    job.result = (uint8_t*)result;
+    job.width = width;
+    job.stride = stride;
+    job.rowBytes = (size_t)width * 4u;
+    job.outRowBytes = (size_t)(width / 4u) * 8u;
+    job.blockRows = height / 4u;
+    job.stripRows = strip_rows_for(job.rowBytes, height);
     // Pinned buffers are DMA'd in place; pageable ones go through the pinned staging strips.
-    const bool stageIn = is_pageable(input), stageOut = is_pageable(result);
-    if (stageIn || stageOut) {
-        rc = t_stage.ensure(stageIn ? stripIn : 0, stageOut ? stripOut : 0);
+    job.stageIn = is_pageable(input);
+    job.stageOut = is_pageable(result);
+    return GOOFY_B200_OK;
+}
+
+// The host-pointer pipeline over any number of images: every strip of every image runs stage (if pageable) -> H2D ->
+// kernel -> D2H on the stream of its slot, slots taken round-robin, so the copies of one strip (or one small image)
+// overlap the kernel and the copies of its neighbours.  Returns when every result is in place.
+int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
+{
+    size_t needIn = 0, needOut = 0, needStageIn = 0, needStageOut = 0;
+    for (uint32_t j = 0; j < nJobs; ++j) {
+        const HostJob& J = jobs[j];
+        if (J.blockRows == 0u) continue;
+        const size_t in = (size_t)J.stripRows * 4u * J.rowBytes, out = (size_t)J.stripRows * J.outRowBytes;
+        needIn = in > needIn ? in : needIn;
+        needOut = out > needOut ? out : needOut;
+        if (J.stageIn && in > needStageIn) needStageIn = in;
+        if (J.stageOut && out > needStageOut) needStageOut = out;
+    }
+    if (needIn == 0) return GOOFY_B200_OK;
+    int rc = t_pipe.prepare(dev, needIn, needOut);
+    if (rc != GOOFY_B200_OK) return rc;
+    if (needStageIn || needStageOut) {
+        rc = t_stage.ensure(needStageIn, needStageOut);
         if (rc != GOOFY_B200_OK) return rc;
     }
-    struct Pending { uint32_t r0 = 0, rows = 0; bool live = false; } pending[kSlots];
+
+    struct Pending { const HostJob* job = nullptr; uint32_t r0 = 0, rows = 0; } pending[kSlots];
     auto retire = [&](int slot) -> int {  // wait for the slot's strip and hand its blocks to the caller
-        if (!pending[slot].live) return GOOFY_B200_OK;
+        const HostJob* J = pending[slot].job;
+        if (!J) return GOOFY_B200_OK;
         GB_CUDA(cudaStreamSynchronize(t_pipe.stream[slot]));
-        if (stageOut)
-            CopyPool::get().copy1d((uint8_t*)result + (size_t)pending[slot].r0 * outRowBytes, (const uint8_t*)t_stage.out[slot],
-                                   (size_t)pending[slot].rows * outRowBytes);
-        pending[slot].live = false;
+        if (J->stageOut)
+            CopyPool::get().copy1d(J->result + (size_t)pending[slot].r0 * J->outRowBytes, (const uint8_t*)t_stage.out[slot],
+                                   (size_t)pending[slot].rows * J->outRowBytes);
+        pending[slot].job = nullptr;
         return GOOFY_B200_OK;
     };
-
     // One strip: stage (if pageable) -> H2D -> kernel -> D2H, all on the slot's stream.
-    auto issue = [&](int slot, uint32_t r0, uint32_t rows) -> int {
+    auto issue = [&](int slot, const HostJob& J, uint32_t r0, uint32_t rows) -> int {
         cudaStream_t s = t_pipe.stream[slot];
-        const uint8_t* src = (const uint8_t*)input + (size_t)r0 * 4u * stride;
-        if (stageIn || stageOut) {
-            const int r = retire(slot);  // the staging strips of this slot are about to be reused
+        const uint8_t* src = J.input + (size_t)r0 * 4u * J.stride;
+        // the staging strips of this slot are about to be reused (pinned results: stream order protects the device scratch)
+        if (pending[slot].job && (J.stageIn || J.stageOut || pending[slot].job->stageOut)) {
+            const int r = retire(slot);
             if (r != GOOFY_B200_OK) return r;
         }
-        if (stageIn) {
-            CopyPool::get().copy2d((uint8_t*)t_stage.in[slot], rowBytes, src, stride, rowBytes, (size_t)rows * 4u);
-            GB_CUDA(cudaMemcpyAsync(t_pipe.dIn[slot], t_stage.in[slot], (size_t)rows * 4u * rowBytes, cudaMemcpyHostToDevice, s));
+        if (J.stageIn) {
+            CopyPool::get().copy2d((uint8_t*)t_stage.in[slot], J.rowBytes, src, J.stride, J.rowBytes, (size_t)rows * 4u);
+            GB_CUDA(cudaMemcpyAsync(t_pipe.dIn[slot], t_stage.in[slot], (size_t)rows * 4u * J.rowBytes, cudaMemcpyHostToDevice, s));
         } else {
-            // stream order protects the slot's device scratch: its previous strip finished D2H on the same stream
-            GB_CUDA(cudaMemcpy2DAsync(t_pipe.dIn[slot], rowBytes, src, stride, rowBytes, (size_t)rows * 4u, cudaMemcpyHostToDevice, s));
+            GB_CUDA(cudaMemcpy2DAsync(t_pipe.dIn[slot], J.rowBytes, src, J.stride, J.rowBytes, (size_t)rows * 4u, cudaMemcpyHostToDevice, s));
         }
-        const int r = encode_any(codec, t_pipe.dOut[slot], t_pipe.dIn[slot], width, rows * 4u, (uint32_t)rowBytes, 0, 0, 1, s);
+        const int r = encode_any(codec, t_pipe.dOut[slot], t_pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s);
         if (r != GOOFY_B200_OK) return r;
-        GB_CUDA(cudaMemcpyAsync(stageOut ? t_stage.out[slot] : (void*)((uint8_t*)result + (size_t)r0 * outRowBytes), t_pipe.dOut[slot],
-                                (size_t)rows * outRowBytes, cudaMemcpyDeviceToHost, s));
+        GB_CUDA(cudaMemcpyAsync(J.stageOut ? t_stage.out[slot] : (void*)(J.result + (size_t)r0 * J.outRowBytes), t_pipe.dOut[slot],
+                                (size_t)rows * J.outRowBytes, cudaMemcpyDeviceToHost, s));
+        pending[slot].job = &J;
         pending[slot].r0 = r0;
         pending[slot].rows = rows;
-        pending[slot].live = true;
         return GOOFY_B200_OK;
     };
-    // On failure nothing may still be reading `input` or writing `result` when the caller gets control back.
+    // On failure nothing may still be reading an input or writing a result when the caller gets control back.
     auto fail = [&](int code) -> int {
         for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(t_pipe.stream[i]);
         cudaGetLastError();
@@ -191,17 +227,49 @@ int encode_host(int codec, void* result, const void* input, uint32_t width, uint
     };
 
     int slot = 0;
-    for (uint32_t r0 = 0; r0 < blockRows; r0 += stripRows, slot = (slot + 1) % kSlots) {
-        const uint32_t rows = blockRows - r0 < stripRows ? blockRows - r0 : stripRows;
-        rc = issue(slot, r0, rows);
-        if (rc != GOOFY_B200_OK) return fail(rc);
+    for (uint32_t j = 0; j < nJobs; ++j) {
+        const HostJob& J = jobs[j];
+        for (uint32_t r0 = 0; r0 < J.blockRows; r0 += J.stripRows, slot = (slot + 1) % kSlots) {
+            const uint32_t rows = J.blockRows - r0 < J.stripRows ? J.blockRows - r0 : J.stripRows;
+            rc = issue(slot, J, r0, rows);
+            if (rc != GOOFY_B200_OK) return fail(rc);
+        }
     }
-    // drain in strip order (the oldest outstanding strip is in the slot the loop would use next)
+    // drain in issue order (the oldest outstanding strip is in the slot the loop would use next)
     for (int i = 0; i < kSlots; ++i, slot = (slot + 1) % kSlots) {
         rc = retire(slot);
         if (rc != GOOFY_B200_OK) return fail(rc);
     }
     return GOOFY_B200_OK;
+}
+
+int encode_host(int codec, void* result, const void* input, uint32_t width, uint32_t height, uint32_t stride)
+{
+    if (!is_codec(codec)) return GOOFY_B200_E_CODEC;
+    HostJob job;
+    int rc = make_host_job(codec, result, input, width, height, stride, job);
+    if (rc != GOOFY_B200_OK || job.blockRows == 0u) return rc;
+    int dev = -1;
+    rc = ensure_device_ready(&dev);
+    if (rc != GOOFY_B200_OK) return rc;
+    return run_host_jobs(codec, &job, 1, dev);
+}
+
+// n host images through ONE pipeline: every image is validated before anything is started.
+int encode_host_batch(int codec, const GoofyB200Image* images, uint32_t n)
+{
+    if (!is_codec(codec)) return GOOFY_B200_E_CODEC;
+    if (n == 0u) return GOOFY_B200_OK;
+    if (!images) return GOOFY_B200_E_NULL;
+    std::vector<HostJob> jobs(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const int rc = make_host_job(codec, images[i].dst, images[i].src, images[i].width, images[i].height, images[i].stride, jobs[i]);
+        if (rc != GOOFY_B200_OK) return rc;
+    }
+    int dev = -1;
+    const int rc = ensure_device_ready(&dev);
+    if (rc != GOOFY_B200_OK) return rc;
+    return run_host_jobs(codec, jobs.data(), n, dev);
 }
 
 }  // namespace

@@ -104,6 +104,12 @@ int goofy_b200_compress_etc1_floatref(unsigned char* result, const unsigned char
 int goofy_b200_encode_host(int codec, void* result, const void* input, uint32_t width, uint32_t height,
                            uint32_t stride);
 
+/* n host images (src / dst are HOST pointers here, `device` is ignored) through one pipeline on the calling thread's
+ * current device: the copies and kernels of neighbouring images overlap, which a loop of single-image calls (each of
+ * which waits for its own result) cannot do -- the host-side batch for the reference harness's per-image loop
+ * (Src/main.cpp:646-743).  Every image is validated before anything starts; returns when all results are in place. */
+int goofy_b200_encode_host_batch(int codec, const GoofyB200Image* images, uint32_t n_images);
+
 /* ---- device-resident API: pointers are device memory on the current device; asynchronous
  *      on `stream` (a cudaStream_t, NULL = default stream); no allocation, no sync ---- */
 int goofy_b200_encode_device(int codec, void* d_result, const void* d_input, uint32_t width, uint32_t height,

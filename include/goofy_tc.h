@@ -99,6 +99,12 @@ inline int encodeSharded(Codec codec, unsigned char* result, const unsigned char
     return goofy_b200_encode_sharded_host(codec, result, input, width, height, stride, nGpus);
 }
 
+// n HOST images (Image::src / dst are host pointers) through one pipeline: copies and kernels of neighbouring images overlap.
+inline int encodeHostBatch(Codec codec, const Image* images, uint32_t nImages)
+{
+    return goofy_b200_encode_host_batch(codec, images, nImages);
+}
+
 // The step after the encoder (Src/main.cpp:561-613, :403-469): blocks -> RGBA8 on the device ...
 inline int decode(Codec codec, void* dRgba, const void* dBlocks, uint32_t width, uint32_t height, uint32_t stride,
                   void* stream = nullptr)

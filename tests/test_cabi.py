@@ -75,6 +75,19 @@ def test_no_cpu_fallback_without_a_gpu():
     assert gb.compressDXT1(out, img, 32, 32, 128) == -7   # GOOFY_B200_E_DEVICE, output untouched
     assert not out.any()
     assert gb.encode_sharded_host(0, out, img, 32, 32, 128, 0) == -7
+    assert gb.encode_host_batch(0, [(img, out, 32, 32, 128)]) == -7
+
+
+def test_host_batch_validates_every_image_before_starting():
+    out = np.zeros(512, dtype=np.uint8)
+    img = np.zeros(32 * 32 * 4, dtype=np.uint8)
+    assert gb.encode_host_batch(0, []) == 0
+    assert gb.encode_host_batch(9, [(img, out, 32, 32, 128)]) == -6                              # codec
+    assert gb.encode_host_batch(0, [(img, out, 32, 32, 128), (img, out, 24, 32, 128)]) == -1     # second image: width % 16
+    assert gb.encode_host_batch(1, [(img, out, 32, 30, 128)]) == -2                              # height % 4
+    assert gb.encode_host_batch(0, [(img, out, 32, 32, 64)]) == -5                               # stride < width * 4
+    assert gb.encode_host_batch(0, [(None, out, 32, 32, 128)]) == -3                             # null input
+    assert not out.any()
 
 
 def test_strip_partition_matches_python_twin():

@@ -621,6 +621,37 @@ def test_host_api_pinned_and_pageable_buffers(codec, oracle):
             assert np.array_equal(out.numpy(), want)
 
 
+@pytest.mark.parametrize("codec", CODECS)
+def test_host_batch_mixed_buffers_and_shapes(codec, oracle):
+    """goofy_b200_encode_host_batch: many host images through one pipeline -- pageable and pinned buffers mixed,
+    padded strides, images from one block row to several strips, an empty image in the middle."""
+    shapes = [(16, 4, 0), (768, 512, 0), (272, 12, 64), (2048, 1024, 0), (64, 64, 0), (0, 0, 0), (1040, 68, 16), (4096, 1028, 0)]
+    items, keep, wants = [], [], []
+    for i, (w, h, pad) in enumerate(shapes):
+        stride = w * 4 + pad
+        img = splitmix_rgba(max(w * h, 1), seed=700 + i)[: w * h * 4]
+        if w:
+            rows = np.full((h, stride), 0xAB, dtype=np.uint8)
+            rows[:, : w * 4] = img.reshape(h, w * 4)
+        else:
+            rows = np.zeros((1, 16), dtype=np.uint8)
+        if i % 2:   # pinned input / pinned output for every other image
+            src = torch.from_numpy(rows.reshape(-1).copy()).pin_memory()
+            dst = torch.zeros(max(w * h // 2, 8), dtype=torch.uint8).pin_memory()
+        else:
+            from oracle.oracle import aligned_copy
+            src = aligned_copy(rows.reshape(-1))
+            dst = np.zeros(max(w * h // 2, 8), dtype=np.uint8)
+        keep.append((src, dst))
+        items.append((src, dst, w, h, stride))
+        wants.append(oracle.compress(codec, img, w, h)[1] if w else None)
+    assert gb.encode_host_batch(codec, items) == 0
+    for (src, dst, w, h, stride), want in zip(items, wants):
+        if want is not None:
+            got = dst.numpy() if hasattr(dst, "numpy") else dst
+            assert np.array_equal(got[: w * h // 2], want), (w, h)
+
+
 @pytest.mark.parametrize("path", ["LOAD_DIRECT", "LOAD_ONESHOT", "LOAD_ASYNC", "LOAD_TMA"])
 @pytest.mark.parametrize("codec", CODECS)
 def test_every_load_layer_is_bit_exact(codec, path, oracle):

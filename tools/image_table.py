@@ -24,6 +24,7 @@ ref = Reference()
 names = image_names()
 rows = []
 dev_imgs = []
+host_imgs = []
 for n in names:
     img = load_test_image(n)
     h, w = img.shape[:2]
@@ -67,6 +68,7 @@ for n in names:
                     "b200_host_call_mps": w * h / host_best / 1e6, "b200_host_call_us": host_best * 1e6}
     rows.append(row)
     dev_imgs.append((d_src, w, h))
+    host_imgs.append((host, w, h))
 
 # all images in one ragged-batch launch
 total_px = sum(w * h for _, w, h in dev_imgs)
@@ -87,9 +89,23 @@ for codec, key in ((DXT1, "dxt1"), (ETC1, "etc1")):
         best = min(best, e0.elapsed_time(e1) / 50 * 1e-3)
     batch[key] = {"mps": total_px / best / 1e6, "us": best * 1e6}
 
+# all images through ONE host-pointer call (goofy_b200_encode_host_batch): pageable buffers in and out, wall clock
+host_batch = {}
+for codec, key in ((DXT1, "dxt1"), (ETC1, "etc1")):
+    outs = [np.zeros(w * h // 2, dtype=np.uint8) for _, w, h in host_imgs]
+    items = [(hst.reshape(-1), o, w, h, w * 4) for (hst, w, h), o in zip(host_imgs, outs)]
+    gb.check(gb.encode_host_batch(codec, items))
+    ok = all(np.array_equal(o, ref.compress_mt(codec, hst, w, h, w * 4, 1)[1]) for (hst, w, h), o in zip(host_imgs, outs))
+    best = 1e9
+    for _ in range(20):
+        t0 = time.perf_counter()
+        gb.check(gb.encode_host_batch(codec, items))
+        best = min(best, time.perf_counter() - t0)
+    host_batch[key] = {"mps": total_px / best / 1e6, "us": best * 1e6, "bit_exact": bool(ok)}
+
 out_dir = ROOT / "gpurun_out"
 out_dir.mkdir(exist_ok=True)
-(out_dir / "images.json").write_text(json.dumps({"images": rows, "ragged_batch_all_images": batch, "total_pixels": total_px}, indent=1))
+(out_dir / "images.json").write_text(json.dumps({"images": rows, "ragged_batch_all_images": batch, "host_batch_all_images": host_batch, "total_pixels": total_px}, indent=1))
 with open(out_dir / "images.md", "w") as f:
     f.write("# Test images (BASELINE.json configs[0]): reference CPU vs B200, per image\n\n")
     f.write("CPU = unmodified `goofy::compress*` (-O2 -msse2), one thread, best of 128 calls (the reference harness protocol).\n"
@@ -108,5 +124,8 @@ with open(out_dir / "images.md", "w") as f:
     f.write(f"| **mean of {len(rows)}** | | | {md:.3f} | {me:.3f} | {cd:.0f} | {ce:.0f} | | | {hd:.0f} | {he:.0f} |\n")
     f.write(f"\nAll {len(rows)} images ({total_px / 1e6:.1f} MP) in ONE ragged-batch launch (`goofy_b200_encode_batch_device`): "
             f"DXT1 {batch['dxt1']['us']:.1f} us = {batch['dxt1']['mps']:.0f} MP/s, ETC1s {batch['etc1']['us']:.1f} us = {batch['etc1']['mps']:.0f} MP/s.\n")
+    f.write(f"\nAll {len(rows)} images through ONE host-pointer call (`goofy_b200_encode_host_batch`, pageable buffers in and out, wall clock): "
+            f"DXT1 {host_batch['dxt1']['us']:.0f} us = {host_batch['dxt1']['mps']:.0f} MP/s, ETC1s {host_batch['etc1']['us']:.0f} us = "
+            f"{host_batch['etc1']['mps']:.0f} MP/s (bit-exact: {host_batch['dxt1']['bit_exact'] and host_batch['etc1']['bit_exact']}).\n")
     f.write("\nSURVEY.md section 6.2 measured mean psnrRGB 36.747 / 36.050 over the same 38 images with the reference's own decoder.\n")
 print(open(out_dir / "images.md").read()[-900:])
