@@ -136,6 +136,12 @@ def encode_host(codec: int, result, input, width: int, height: int, stride: int)
                                                   width, height, stride))
 
 
+def encode_dual_host(result_dxt1, result_etc1, input, width: int, height: int, stride: int) -> int:
+    """DXT1 and ETC1s of one host image from a single upload (4 B/px over PCIe instead of 8)."""
+    return int(_lib.load().goofy_b200_encode_dual_host(_host_ptr(result_dxt1, True), _host_ptr(result_etc1, True),
+                                                       _host_ptr(input, False), width, height, stride))
+
+
 def encode_host_batch(codec: int, images) -> int:
     """images: iterable of (input, result, width, height, stride) with HOST buffers (numpy uint8 arrays or pinned
     torch tensors).  One pipeline for all of them: copies and kernels of neighbouring images overlap."""

@@ -85,6 +85,12 @@ int goofy_b200_encode_host(int codec, void* result, const void* input, uint32_t 
     return encode_host(codec, result, input, width, height, stride);
 }
 
+int goofy_b200_encode_dual_host(void* result_dxt1, void* result_etc1, const void* input, uint32_t width, uint32_t height,
+                                uint32_t stride)
+{
+    return encode_dual_host(result_dxt1, result_etc1, input, width, height, stride);
+}
+
 int goofy_b200_encode_host_batch(int codec, const GoofyB200Image* images, uint32_t n_images)
 {
     return encode_host_batch(codec, images, n_images);

@@ -111,6 +111,8 @@ bool is_pageable(const void* p)
 struct HostJob {
     const uint8_t* input = nullptr;
     uint8_t* result = nullptr;
+    uint8_t* result2 = nullptr;   // dual-output jobs: ETC1s blocks (result holds the DXT1 blocks); null otherwise
+    bool stageOut2 = false;
     uint32_t width = 0, stride = 0, blockRows = 0, stripRows = 0;
     size_t rowBytes = 0, outRowBytes = 0;
     bool stageIn = false, stageOut = false;
@@ -170,11 +172,12 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
     for (uint32_t j = 0; j < nJobs; ++j) {
         const HostJob& J = jobs[j];
         if (J.blockRows == 0u) continue;
-        const size_t in = (size_t)J.stripRows * 4u * J.rowBytes, out = (size_t)J.stripRows * J.outRowBytes;
+        // dual-output jobs keep their second result in the upper half of the slot's output scratch / staging strip
+        const size_t in = (size_t)J.stripRows * 4u * J.rowBytes, out = (size_t)J.stripRows * J.outRowBytes * (J.result2 ? 2u : 1u);
         needIn = in > needIn ? in : needIn;
         needOut = out > needOut ? out : needOut;
         if (J.stageIn && in > needStageIn) needStageIn = in;
-        if (J.stageOut && out > needStageOut) needStageOut = out;
+        if ((J.stageOut || J.stageOut2) && out > needStageOut) needStageOut = out;
     }
     if (needIn == 0) return GOOFY_B200_OK;
     int rc = t_pipe.prepare(dev, needIn, needOut);
@@ -192,6 +195,10 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         if (J->stageOut)
             CopyPool::get().copy1d(J->result + (size_t)pending[slot].r0 * J->outRowBytes, (const uint8_t*)t_stage.out[slot],
                                    (size_t)pending[slot].rows * J->outRowBytes);
+        if (J->stageOut2)
+            CopyPool::get().copy1d(J->result2 + (size_t)pending[slot].r0 * J->outRowBytes,
+                                   (const uint8_t*)t_stage.out[slot] + (size_t)J->stripRows * J->outRowBytes,
+                                   (size_t)pending[slot].rows * J->outRowBytes);
         pending[slot].job = nullptr;
         return GOOFY_B200_OK;
     };
@@ -200,7 +207,7 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         cudaStream_t s = t_pipe.stream[slot];
         const uint8_t* src = J.input + (size_t)r0 * 4u * J.stride;
         // the staging strips of this slot are about to be reused (pinned results: stream order protects the device scratch)
-        if (pending[slot].job && (J.stageIn || J.stageOut || pending[slot].job->stageOut)) {
+        if (pending[slot].job && (J.stageIn || J.stageOut || J.stageOut2 || pending[slot].job->stageOut || pending[slot].job->stageOut2)) {
             const int r = retire(slot);
             if (r != GOOFY_B200_OK) return r;
         }
@@ -210,10 +217,16 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         } else {
             GB_CUDA(cudaMemcpy2DAsync(t_pipe.dIn[slot], J.rowBytes, src, J.stride, J.rowBytes, (size_t)rows * 4u, cudaMemcpyHostToDevice, s));
         }
-        const int r = encode_any(codec, t_pipe.dOut[slot], t_pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s);
+        const size_t half = (size_t)J.stripRows * J.outRowBytes;   // where a dual-output job keeps its ETC1s blocks
+        uint8_t* dOut = (uint8_t*)t_pipe.dOut[slot];
+        const int r = J.result2 ? encode_uniform(gb::kDual, dOut, dOut + half, t_pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s)
+                                : encode_any(codec, dOut, t_pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s);
         if (r != GOOFY_B200_OK) return r;
-        GB_CUDA(cudaMemcpyAsync(J.stageOut ? t_stage.out[slot] : (void*)(J.result + (size_t)r0 * J.outRowBytes), t_pipe.dOut[slot],
+        GB_CUDA(cudaMemcpyAsync(J.stageOut ? t_stage.out[slot] : (void*)(J.result + (size_t)r0 * J.outRowBytes), dOut,
                                 (size_t)rows * J.outRowBytes, cudaMemcpyDeviceToHost, s));
+        if (J.result2)
+            GB_CUDA(cudaMemcpyAsync(J.stageOut2 ? (void*)((uint8_t*)t_stage.out[slot] + half) : (void*)(J.result2 + (size_t)r0 * J.outRowBytes),
+                                    dOut + half, (size_t)rows * J.outRowBytes, cudaMemcpyDeviceToHost, s));
         pending[slot].job = &J;
         pending[slot].r0 = r0;
         pending[slot].rows = rows;
@@ -253,6 +266,21 @@ int encode_host(int codec, void* result, const void* input, uint32_t width, uint
     rc = ensure_device_ready(&dev);
     if (rc != GOOFY_B200_OK) return rc;
     return run_host_jobs(codec, &job, 1, dev);
+}
+
+// Both codecs from one upload of a host image: 4 B/px over the link instead of 8.
+int encode_dual_host(void* resultDxt1, void* resultEtc1, const void* input, uint32_t width, uint32_t height, uint32_t stride)
+{
+    HostJob job;
+    int rc = make_host_job(GOOFY_B200_DXT1, resultDxt1, input, width, height, stride, job);
+    if (rc != GOOFY_B200_OK || job.blockRows == 0u) return rc;
+    if (!resultEtc1) return GOOFY_B200_E_NULL;
+    job.result2 = (uint8_t*)resultEtc1;
+    job.stageOut2 = is_pageable(resultEtc1);
+    int dev = -1;
+    rc = ensure_device_ready(&dev);
+    if (rc != GOOFY_B200_OK) return rc;
+    return run_host_jobs(GOOFY_B200_DXT1, &job, 1, dev);
 }
 
 // n host images through ONE pipeline: every image is validated before anything is started.

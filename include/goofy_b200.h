@@ -104,6 +104,11 @@ int goofy_b200_compress_etc1_floatref(unsigned char* result, const unsigned char
 int goofy_b200_encode_host(int codec, void* result, const void* input, uint32_t width, uint32_t height,
                            uint32_t stride);
 
+/* Both codecs from ONE upload of a host image (the dual-output kernel behind the host pipeline): 4 B/px cross the link
+ * instead of 8 for two single-codec calls.  Same argument checks and codes as the single-codec host calls. */
+int goofy_b200_encode_dual_host(void* result_dxt1, void* result_etc1, const void* input, uint32_t width, uint32_t height,
+                                uint32_t stride);
+
 /* n host images (src / dst are HOST pointers here, `device` is ignored) through one pipeline on the calling thread's
  * current device: the copies and kernels of neighbouring images overlap, which a loop of single-image calls (each of
  * which waits for its own result) cannot do -- the host-side batch for the reference harness's per-image loop

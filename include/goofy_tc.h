@@ -99,6 +99,13 @@ inline int encodeSharded(Codec codec, unsigned char* result, const unsigned char
     return goofy_b200_encode_sharded_host(codec, result, input, width, height, stride, nGpus);
 }
 
+// DXT1 and ETC1s of one HOST image from a single upload.
+inline int encodeDualHost(unsigned char* resultDxt1, unsigned char* resultEtc1, const unsigned char* input, uint32_t width,
+                          uint32_t height, uint32_t stride)
+{
+    return goofy_b200_encode_dual_host(resultDxt1, resultEtc1, input, width, height, stride);
+}
+
 // n HOST images (Image::src / dst are host pointers) through one pipeline: copies and kernels of neighbouring images overlap.
 inline int encodeHostBatch(Codec codec, const Image* images, uint32_t nImages)
 {

@@ -76,6 +76,7 @@ def test_no_cpu_fallback_without_a_gpu():
     assert not out.any()
     assert gb.encode_sharded_host(0, out, img, 32, 32, 128, 0) == -7
     assert gb.encode_host_batch(0, [(img, out, 32, 32, 128)]) == -7
+    assert gb.encode_dual_host(out, out, img, 32, 32, 128) == -7
 
 
 def test_host_batch_validates_every_image_before_starting():
@@ -87,6 +88,8 @@ def test_host_batch_validates_every_image_before_starting():
     assert gb.encode_host_batch(1, [(img, out, 32, 30, 128)]) == -2                              # height % 4
     assert gb.encode_host_batch(0, [(img, out, 32, 32, 64)]) == -5                               # stride < width * 4
     assert gb.encode_host_batch(0, [(None, out, 32, 32, 128)]) == -3                             # null input
+    assert gb.encode_dual_host(out, out, img, 24, 32, 128) == -1 and gb.encode_dual_host(out, out, img, 32, 30, 128) == -2
+    assert gb.encode_dual_host(out, None, img, 32, 32, 128) == -3 and gb.encode_dual_host(out, out, img, 0, 0, 0) == 0
     assert not out.any()
 
 

@@ -621,6 +621,35 @@ def test_host_api_pinned_and_pageable_buffers(codec, oracle):
             assert np.array_equal(out.numpy(), want)
 
 
+@pytest.mark.parametrize("shape", [(16, 4, 0), (768, 512, 0), (1040, 68, 32), (4096, 2052, 0)])
+@pytest.mark.parametrize("pinned", [(False, False, False), (True, True, True), (False, True, False), (True, False, True)])
+def test_dual_output_host_call(shape, pinned, oracle):
+    """goofy_b200_encode_dual_host: both codecs from one upload, every mix of pageable / pinned buffers (input, DXT1
+    result, ETC1s result), one block row up to several strips, padded stride."""
+    from oracle.oracle import aligned_copy
+    w, h, pad = shape
+    stride = w * 4 + pad
+    img = splitmix_rgba(w * h, seed=w + h)
+    rows = np.full((h, stride), 0x5A, dtype=np.uint8)
+    rows[:, : w * 4] = img.reshape(h, w * 4)
+
+    def buf(n, pin, fill=None):
+        if pin:
+            t = torch.zeros(n, dtype=torch.uint8).pin_memory()
+            if fill is not None:
+                t.numpy()[:] = fill
+            return t
+        return aligned_copy(fill) if fill is not None else np.zeros(n, dtype=np.uint8)
+
+    src = buf(rows.size, pinned[0], rows.reshape(-1))
+    d1, d2 = buf(w * h // 2, pinned[1]), buf(w * h // 2, pinned[2])
+    assert gb.encode_dual_host(d1, d2, src, w, h, stride) == 0
+    g1 = d1.numpy() if hasattr(d1, "numpy") else d1
+    g2 = d2.numpy() if hasattr(d2, "numpy") else d2
+    assert np.array_equal(g1, oracle.compress(DXT1, img, w, h)[1])
+    assert np.array_equal(g2, oracle.compress(ETC1, img, w, h)[1])
+
+
 @pytest.mark.parametrize("codec", CODECS)
 def test_host_batch_mixed_buffers_and_shapes(codec, oracle):
     """goofy_b200_encode_host_batch: many host images through one pipeline -- pageable and pinned buffers mixed,
