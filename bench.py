@@ -47,6 +47,12 @@ def parse_args():
     return ap.parse_args()
 
 
+def metric_name(args) -> str:
+    """ONE metric string for both arms (the driver compares them literally); where the pixels live
+    (device-resident / host-resident) is stated in config.workload only."""
+    return f"MP/s {args.codec.upper()} encode, {args.size}x{args.size} RGBA8"
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -253,7 +259,7 @@ def run_reference_arm(args):
     sample = f"{args.steps} x one {size}x{size} RGBA8 texture ({args.codec}), row-parallel over {threads} threads"
     line = {
         "impl": "reference",
-        "metric": f"MP/s {args.codec.upper()} encode, {size}x{size} RGBA8",
+        "metric": metric_name(args),
         "value": mps, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
@@ -437,7 +443,7 @@ def run_b200_arm(args):
 
     if rank == 0:
         line = {
-            "metric": f"MP/s {args.codec.upper()} encode, {size}x{size} RGBA8, device-resident",
+            "metric": metric_name(args),
             "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",

@@ -44,3 +44,10 @@ def test_b200_arm_has_no_cpu_fallback():
                          timeout=300, cwd=str(ROOT))
     assert out.returncode != 0 and out.stdout.strip() == ""
     assert "no CUDA device" in out.stderr
+
+
+def test_both_arms_print_the_same_metric_string():
+    """The driver computes the headline ratio only when `metric`, `unit` and direction of the two arms are equal."""
+    src = (ROOT / "bench.py").read_text()
+    assert src.count('"metric": metric_name(args)') == 2
+    assert src.count('"metric":') == 2
