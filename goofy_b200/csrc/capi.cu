@@ -10,6 +10,7 @@
 // without a CUDA device every call returns an error code.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>

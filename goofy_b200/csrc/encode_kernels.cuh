@@ -56,17 +56,39 @@ struct EncodeParams {
     uint32_t bw, bh;     // image size in blocks
     uint32_t stride;     // bytes between pixel rows
     uint32_t by0;        // first block row handled by this launch (grid.y chunking)
+    uint32_t firstWave;  // CTAs (in launch order) that warm L2 with their first tile before griddepcontrol.wait; 0 = none
     uint64_t srcPitch;   // bytes between images
     uint64_t dstPitch;
 };
 
-// ETC1 control words by clamped brightness range; filled once per device by the host
-// (same content as the reference's table, goofy_tc.h:1040-1057, generated not copied).
-__device__ uint32_t g_etc1ControlLut[256];
-
-__global__ void fill_control_lut_kernel()
+// ETC1 control words by clamped brightness range, staged in shared memory by every CTA from a table in device
+// memory.  The table is a `__device__ const` object with a CONSTANT initialiser (built at compile time from the
+// seven thresholds), so it is part of the module image: there is no per-device initialisation kernel, the first
+// call on a device neither synchronises it nor breaks a stream capture.  Same content as the reference's table
+// (goofy_tc.h:1040-1057), generated, not copied.  [1] = the float-reference flavour's thresholds
+// (Src/goofy_tc_reference.cpp:684-720).  (Computing the entries in every CTA instead was measured 3-5 % slower on
+// the ETC1s / dual-output kernels: seventeen more ALU-pipe instructions per thread and CTA.)
+struct ControlTables {
+    uint32_t word[2][256];
+};
+constexpr ControlTables make_control_tables()
 {
-    g_etc1ControlLut[threadIdx.x] = etc1_control_word(threadIdx.x);
+    ControlTables t = {};
+    for (uint32_t r = 0; r < 256u; ++r) {
+        const uint32_t cw = (r >= 22u) + (r >= 44u) + (r >= 74u) + (r >= 106u) + (r >= 152u) + (r >= 182u) + (r >= 254u);
+        const uint32_t cwRef = (r > 10u) + (r > 21u) + (r > 36u) + (r > 52u) + (r > 75u) + (r > 90u) + (r > 126u);
+        t.word[0][r] = (cw * 36u + 3u) << 24;
+        t.word[1][r] = (cwRef * 36u + 3u) << 24;
+    }
+    return t;
+}
+__device__ const ControlTables g_controlTables = make_control_tables();
+
+template <bool REF, int NTHREADS>
+__device__ __forceinline__ void stage_control_lut(uint32_t* lut, uint32_t t)
+{
+#pragma unroll
+    for (uint32_t i = t; i < 256u; i += NTHREADS) lut[i] = g_controlTables.word[REF ? 1 : 0][i];
 }
 
 // Programmatic dependent launch: when the host launches with programmatic stream serialisation, the
@@ -76,6 +98,12 @@ __global__ void fill_control_lut_kernel()
 // (back-to-back 45 us launches otherwise lose ~7 % to it).  Both are no-ops for a normal launch.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Warm L2 with one 128-byte line.  Issued by the first wave of CTAs BEFORE griddepcontrol.wait: a prefetch has no
+// architectural effect (L2 is the coherence point, so a line the previous kernel writes afterwards is still read
+// correctly), but DRAM starts streaming this launch's first tiles while the previous kernel is still draining its
+// last wave, instead of idling until every CTA of it has retired.
+__device__ __forceinline__ void prefetch_l2(const uint8_t* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint4 load_row(const uint8_t* p)
 {
@@ -131,18 +159,12 @@ __global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) enco
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     pdl_launch_dependents();
-    pdl_wait();
-    if (MODE != kDxt1) {
-        // the launcher always uses GB_TPB threads (x a power of two, x*y == GB_TPB)
-        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
-#pragma unroll
-        for (uint32_t i = t; i < 256u; i += GB_TPB) lut[i] = g_etc1ControlLut[i];
-        __syncthreads();
-    }
+    // the launcher always uses GB_TPB threads (x a power of two, x*y == GB_TPB)
+    if (MODE != kDxt1) stage_control_lut<false, GB_TPB>(lut, threadIdx.y * blockDim.x + threadIdx.x);
 
     const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t by = P.by0 + blockIdx.y * blockDim.y + threadIdx.y;
-    if (bx >= P.bw || by >= P.bh) return;
+    const bool live = bx < P.bw && by < P.bh;
 
     typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type off_t;
     const off_t o0 = (off_t)by * ((off_t)4u * P.stride) + (off_t)(bx * 16u);
@@ -155,6 +177,18 @@ __global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) enco
         dst += (uint64_t)blockIdx.z * P.dstPitch;
         if (MODE == kDual) dst2 += (uint64_t)blockIdx.z * P.dstPitch;
     }
+    if (P.firstWave != 0u) {
+        const uint32_t cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (cta < P.firstWave && live && (threadIdx.x & 7u) == 0u) {   // eight neighbouring threads share a 128-byte line
+            prefetch_l2(src + o0);
+            prefetch_l2(src + o1);
+            prefetch_l2(src + o2);
+            prefetch_l2(src + o3);
+        }
+    }
+    pdl_wait();
+    if (MODE != kDxt1) __syncthreads();
+    if (!live) return;
     const uint4 r0 = load_row(src + o0);
     const uint4 r1 = load_row(src + o1);
     const uint4 r2 = load_row(src + o2);
@@ -163,28 +197,41 @@ __global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) enco
     encode_and_store<MODE>(r0, r1, r2, r3, lut, dst + o, MODE == kDual ? dst2 + o : nullptr);
 }
 
-// Persistent variant for single images and back-to-back batches: the grid is sized to what is
-// resident at once (launcher: SMs x CTAs/SM), blockIdx.x picks the column strip and every CTA
-// walks down the image in steps of gridDim.y * blockDim.y block rows.  The per-thread set-up
+// Row-walking variant: blockIdx.x picks the column strip and every CTA walks down its image in steps of
+// gridDim.y * blockDim.y block rows (the launcher sizes the grid to a few rows per CTA, never fewer CTAs than
+// are resident at once).  PITCHED: blockIdx.z picks the image of a batch laid out at fixed pitches.  The per-thread set-up
 // (indices, control table, constants) is paid once and each further block costs only the
 // pointer bumps -- about 25 fewer instructions per block than one-shot CTAs.
-template <int MODE, bool WIDE>
-__global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) encode_rows_kernel(const EncodeParams P)
+template <int MODE, bool WIDE, bool PITCHED>
+__global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) encode_rows_kernel(const EncodeParams P0)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     pdl_launch_dependents();
-    pdl_wait();
-    if (MODE != kDxt1) {
-        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
-#pragma unroll
-        for (uint32_t i = t; i < 256u; i += GB_TPB) lut[i] = g_etc1ControlLut[i];
-        __syncthreads();
+    if (MODE != kDxt1) stage_control_lut<false, GB_TPB>(lut, threadIdx.y * blockDim.x + threadIdx.x);
+    EncodeParams P = P0;
+    if (PITCHED) {   // grid.z = image of a batch laid out at fixed pitches
+        P.src += (uint64_t)blockIdx.z * P.srcPitch;
+        P.dst += (uint64_t)blockIdx.z * P.dstPitch;
+        if (MODE == kDual) P.dst2 += (uint64_t)blockIdx.z * P.dstPitch;
     }
     const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t by = blockIdx.y * blockDim.y + threadIdx.y;
-    if (bx >= P.bw || by >= P.bh) return;
-
+    const bool live = bx < P.bw && by < P.bh;
     typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type off_t;
+    if (P.firstWave != 0u) {
+        const uint32_t cta = blockIdx.x + gridDim.x * (blockIdx.y + (PITCHED ? gridDim.y * blockIdx.z : 0u));
+        if (cta < P.firstWave && live && (threadIdx.x & 7u) == 0u) {
+            const off_t o0 = (off_t)by * ((off_t)4u * P.stride) + (off_t)(bx * 16u);
+            prefetch_l2(P.src + o0);
+            prefetch_l2(P.src + o0 + P.stride);
+            prefetch_l2(P.src + o0 + 2u * (off_t)P.stride);
+            prefetch_l2(P.src + o0 + 3u * (off_t)P.stride);
+        }
+    }
+    pdl_wait();
+    if (MODE != kDxt1) __syncthreads();
+    if (!live) return;
+
     const uint32_t rowStep = gridDim.y * blockDim.y;
     // Only `by` is carried round the loop; offsets are rebuilt from it (a few IMADs on the
     // otherwise idle multiply pipe) so the loop state stays inside the 32-register budget.
@@ -220,13 +267,12 @@ __global__ void __launch_bounds__(GB_TPB, GB_ASYNC_CTAS(MODE)) encode_rows_async
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     __shared__ __align__(16) uint4 ring[2][4][GB_TPB];  // [stage][pixel row][thread]
     pdl_launch_dependents();
-    pdl_wait();
     const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
     if (MODE != kDxt1) {
-#pragma unroll
-        for (uint32_t i = t; i < 256u; i += GB_TPB) lut[i] = g_etc1ControlLut[i];
+        stage_control_lut<false, GB_TPB>(lut, t);
         __syncthreads();
     }
+    pdl_wait();
     const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t by = blockIdx.y * blockDim.y + threadIdx.y;
     if (bx >= P.bw || by >= P.bh) return;
@@ -262,18 +308,13 @@ __global__ void __launch_bounds__(GB_TPB, GB_ASYNC_CTAS(MODE)) encode_rows_async
 }
 
 // Float-reference flavour (goofyRef::, block_codec.cuh "float-reference flavour"): one-shot CTAs,
-// any width that is a multiple of 4.  `lutRef` is the goofyRef control table by brightRange.
-__device__ uint32_t g_etc1ControlLutRef[256];
-
-__global__ void fill_control_lut_ref_kernel() { g_etc1ControlLutRef[threadIdx.x] = etc1_control_word_ref(threadIdx.x); }
-
+// any width that is a multiple of 4.  the control table is goofyRef's, by brightRange.
 template <int CODEC>
 __global__ void __launch_bounds__(256, 8) encode_floatref_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[CODEC == kDxt1 ? 1 : 256];
     if (CODEC != kDxt1) {
-        const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
-        lut[t] = g_etc1ControlLutRef[t];
+        stage_control_lut<true, 256>(lut, threadIdx.y * blockDim.x + threadIdx.x);
         __syncthreads();
     }
     const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,7 +347,7 @@ __global__ void __launch_bounds__(256, 6) encode_relaxed_kernel(const uint8_t* _
 {
     __shared__ uint32_t lut[CODEC == kDxt1 ? 1 : 256];
     if (CODEC != kDxt1) {
-        lut[threadIdx.x] = FLAVOUR ? g_etc1ControlLutRef[threadIdx.x] : g_etc1ControlLut[threadIdx.x];
+        stage_control_lut<FLAVOUR != 0, 256>(lut, threadIdx.x);
         __syncthreads();
     }
     const uint32_t bw = (width + 3u) / 4u, bh = (height + 3u) / 4u;
@@ -384,8 +425,7 @@ __global__ void __launch_bounds__(kBatchTileX* kBatchTileY, ctas_per_sm(MODE))
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     if (MODE != kDxt1) {
-        const uint32_t t = threadIdx.y * kBatchTileX + threadIdx.x;
-        lut[t] = g_etc1ControlLut[t];
+        stage_control_lut<false, kBatchTileX * kBatchTileY>(lut, threadIdx.y * kBatchTileX + threadIdx.x);
         __syncthreads();
     }
     // largest i with start(i) <= blockIdx.x

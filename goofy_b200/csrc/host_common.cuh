@@ -16,10 +16,10 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? GOOFY_B200_OK : GO
 
 std::atomic<int> g_loadPath{GOOFY_B200_LOAD_AUTO};
 
-// ---- per-device one-time state: the ETC1 control table in device memory ----
+// The calling thread's current device.  There is no per-device initialisation: the kernels compute their control
+// table themselves, so the first call on a device does not synchronise it and the device entry points can be
+// captured into a CUDA graph from their very first use.
 constexpr int kMaxDevices = 64;
-std::once_flag g_lutOnce[kMaxDevices];
-int g_lutStatus[kMaxDevices];
 
 int ensure_device_ready(int* deviceOut = nullptr)
 {
@@ -27,15 +27,8 @@ int ensure_device_ready(int* deviceOut = nullptr)
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) { cudaGetLastError(); return GOOFY_B200_E_DEVICE; }
     if (dev < 0 || dev >= kMaxDevices) return GOOFY_B200_E_DEVICE;
-    std::call_once(g_lutOnce[dev], [dev]() {
-        gb::fill_control_lut_kernel<<<1, 256>>>();
-        gb::fill_control_lut_ref_kernel<<<1, 256>>>();
-        cudaError_t le = cudaGetLastError();
-        if (le == cudaSuccess) le = cudaDeviceSynchronize();
-        g_lutStatus[dev] = cuda_rc(le);
-    });
     if (deviceOut) *deviceOut = dev;
-    return g_lutStatus[dev];
+    return GOOFY_B200_OK;
 }
 
 // Shape checks in the reference's order (goofy_tc.h:1500-1508), then the new ones.

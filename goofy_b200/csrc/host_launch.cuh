@@ -34,10 +34,23 @@ int launch_direct_grid(const gb::EncodeParams& Q, dim3 grid, dim3 block, cudaStr
 }
 
 int sm_count(int dev);
+int env_int(const char* name, int lo, int hi, int fallback);
 
-// Persistent row-walking launch for one (possibly very tall) image.
+// CTAs of a launch that warm L2 with their first tile before griddepcontrol.wait (encode_kernels.cuh: prefetch_l2):
+// the ones resident at once.  GOOFY_B200_L2PF=0 turns it off.
+uint32_t first_wave(uint32_t resident)
+{
+    static const bool on = env_int("GOOFY_B200_L2PF", 0, 1, 1) != 0;
+    return on ? resident : 0u;
+}
+
+// The L2 warm-up before griddepcontrol.wait pays on short launches (a 16384 x 2048 strip: +4-5 %, profiles/r02_shape_ab.md),
+// where the hand-over between two launches is a visible share of the time; long launches skip it.
+constexpr uint32_t kL2PrefetchMaxWaves = 16;
+
+// Row-walking launch: one (possibly very tall) image, or a batch at fixed pitches (grid.z = image).
 template <int MODE>
-int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
+int launch_rows(const gb::EncodeParams& P, uint32_t nImages, cudaStream_t stream, int dev)
 {
     uint32_t tx = 32u;
     while (tx < (uint32_t)GB_TPB && tx < P.bw) tx <<= 1;
@@ -50,7 +63,7 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     // is encoded): +2-3 % over plain loads in every A/B session since it stopped being ALU-bound (r01f sessions 3, 8, 9);
     // the single-codec kernels are faster with plain loads (ETC1s -5 % through the ring)
     const int loadPath = g_loadPath.load(std::memory_order_relaxed);
-    const bool async = loadPath == GOOFY_B200_LOAD_ASYNC || (loadPath == GOOFY_B200_LOAD_AUTO && MODE == gb::kDual);
+    const bool async = nImages == 1u && (loadPath == GOOFY_B200_LOAD_ASYNC || (loadPath == GOOFY_B200_LOAD_AUTO && MODE == gb::kDual));
     const uint32_t resident = async ? (uint32_t)sms * (uint32_t)GB_ASYNC_CTAS(MODE)
                                     : (uint32_t)sms * (uint32_t)gb::ctas_per_sm(MODE) * (256u / (uint32_t)GB_TPB);
     // Each CTA walks a few block rows: enough to amortise the per-thread set-up, few enough that CTAs keep
@@ -58,20 +71,37 @@ int launch_rows(const gb::EncodeParams& P, cudaStream_t stream, int dev)
     // profiles/r01_rows_grid_sweep.txt).  Never fewer CTAs than one resident wave.
     // Measured on the batched 4 x 8192^2 launch: ETC1s 6915 / 7011 / 7010 / 6966 / 6892 GB/s at 2 / 3 / 4 / 6 / 8 rows
     // per CTA; dual-output 5835 / 5932 / 6055 / 6193 / 6293.
-    static const uint32_t rowsEnv = []() { const char* e = getenv("GOOFY_B200_ROWS_PER_CTA"); const int v = e ? atoi(e) : 0; return v > 0 ? (uint32_t)v : 0u; }();
+    static const uint32_t rowsEnv = (uint32_t)env_int("GOOFY_B200_ROWS_PER_CTA", 1, 1 << 20, 0);
     const uint32_t rowsPerCta = rowsEnv ? rowsEnv : (MODE == gb::kDual ? 8u : 4u);
     uint32_t gy = (rowGroups + rowsPerCta - 1u) / rowsPerCta;
-    if (gy < resident / gx) gy = resident / gx;
+    const uint32_t perImage = (resident + nImages - 1u) / nImages;   // this image's share of one resident wave
+    if (gy < perImage / gx) gy = perImage / gx;
     if (gy == 0u) gy = 1u;
     if (gy > rowGroups) gy = rowGroups;
     if (gy > 65535u) gy = 65535u;
-    const dim3 grid(gx, gy, 1), block(tx, ty, 1);
+    const dim3 block(tx, ty, 1);
     const bool narrow = (uint64_t)P.bh * 4u * P.stride + (uint64_t)P.bw * 16u < 0xFFFFFFFFull;
-    if (async)
-        return narrow ? launch_encode(gb::encode_rows_async_kernel<MODE, false>, grid, block, stream, P)
-                      : launch_encode(gb::encode_rows_async_kernel<MODE, true>, grid, block, stream, P);
-    if (narrow) return launch_encode(gb::encode_rows_kernel<MODE, false>, grid, block, stream, P);
-    return launch_encode(gb::encode_rows_kernel<MODE, true>, grid, block, stream, P);
+    for (uint32_t img0 = 0; img0 < nImages; img0 += 65535u) {
+        const uint32_t nz = nImages - img0 < 65535u ? nImages - img0 : 65535u;
+        gb::EncodeParams Q = P;
+        Q.src += (uint64_t)img0 * P.srcPitch;
+        Q.dst += (uint64_t)img0 * P.dstPitch;
+        if (Q.dst2) Q.dst2 += (uint64_t)img0 * P.dstPitch;
+        const dim3 grid(gx, gy, nz);
+        Q.firstWave = (!async && (uint64_t)gx * gy * nz <= (uint64_t)kL2PrefetchMaxWaves * resident) ? first_wave(resident) : 0u;
+        int rc;
+        if (async)
+            rc = narrow ? launch_encode(gb::encode_rows_async_kernel<MODE, false>, grid, block, stream, Q)
+                        : launch_encode(gb::encode_rows_async_kernel<MODE, true>, grid, block, stream, Q);
+        else if (nImages > 1u)
+            rc = narrow ? launch_encode(gb::encode_rows_kernel<MODE, false, true>, grid, block, stream, Q)
+                        : launch_encode(gb::encode_rows_kernel<MODE, true, true>, grid, block, stream, Q);
+        else
+            rc = narrow ? launch_encode(gb::encode_rows_kernel<MODE, false, false>, grid, block, stream, Q)
+                        : launch_encode(gb::encode_rows_kernel<MODE, true, false>, grid, block, stream, Q);
+        if (rc != GOOFY_B200_OK) return rc;
+    }
+    return GOOFY_B200_OK;
 }
 
 template <int MODE>
@@ -85,12 +115,12 @@ int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream, int
     }
     // Load-path policy for AUTO: the DXT1 kernel is HBM-bound either way and
     // one-shot CTAs are marginally faster (6617 vs 6598 GB/s); the ETC1s and dual-output kernels
-    // gain 4-13 % from row-walking CTAs (dual-output: through the cp.async ring, see launch_rows).
+    // gain 4-13 % from row-walking CTAs (dual-output on a single image: through the cp.async ring, see launch_rows).
     const int path = g_loadPath.load(std::memory_order_relaxed);
     const bool rows = path == GOOFY_B200_LOAD_DIRECT || path == GOOFY_B200_LOAD_ASYNC ||
                       (path == GOOFY_B200_LOAD_AUTO && MODE != gb::kDxt1);
-    if (nImages == 1u && rows) return launch_rows<MODE>(P, stream, dev);
-    // one-shot CTAs (pitched batches): threads: x walks blocks along a row (coalescing), y stacks block rows for narrow images
+    if (rows) return launch_rows<MODE>(P, nImages, stream, dev);
+    // one-shot CTAs: threads: x walks blocks along a row (coalescing), y stacks block rows for narrow images
     // (x is a power of two and x*y == GB_TPB: the kernels rely on exactly GB_TPB threads)
     uint32_t tx = 32u;
     while (tx < (uint32_t)GB_TPB && tx < P.bw) tx <<= 1;
@@ -98,6 +128,10 @@ int launch_direct(gb::EncodeParams P, uint32_t nImages, cudaStream_t stream, int
     const dim3 block(tx, ty, 1);
     const uint32_t gx = (P.bw + tx - 1u) / tx;
     const uint32_t rowsPerLaunch = 65535u * ty;
+    const int sms = sm_count(dev);
+    const uint32_t resident = (uint32_t)(sms > 0 ? sms : 148) * (uint32_t)gb::ctas_per_sm(MODE) * (256u / (uint32_t)GB_TPB);
+    const uint64_t totalCtas = (uint64_t)gx * ((P.bh + ty - 1u) / ty) * nImages;
+    P.firstWave = totalCtas <= (uint64_t)kL2PrefetchMaxWaves * resident ? first_wave(resident) : 0u;
     for (uint32_t img0 = 0; img0 < nImages; img0 += 65535u) {
         const uint32_t nz = nImages - img0 < 65535u ? nImages - img0 : 65535u;
         for (uint32_t by0 = 0; by0 < P.bh; by0 += rowsPerLaunch) {
@@ -139,7 +173,8 @@ EncodeTiledFn tensor_map_encoder()
 
 struct DeviceInfo {
     int smCount = 0;
-    int tmaCtasPerSm[3] = {0, 0, 0};  // 0 = not yet configured
+    int tmaCtasPerSm[3][3] = {};  // [mode][log2 RB]; 0 = not yet configured
+    int tmaSmemBytes[3][3] = {};
 };
 DeviceInfo g_devInfo[kMaxDevices];
 std::mutex g_devInfoMutex;
@@ -155,16 +190,19 @@ int sm_count(int dev)
     return di.smCount;
 }
 
-// Depth of the tile ring.  GOOFY_B200_TMA_STAGES overrides it for experiments (2..8).
-uint32_t tma_stages()
+int env_int(const char* name, int lo, int hi, int fallback)
 {
-    static const uint32_t n = []() -> uint32_t {
-        const char* e = getenv("GOOFY_B200_TMA_STAGES");
-        const int v = e ? atoi(e) : 0;
-        return (v >= 2 && v <= gb::kTmaMaxStages) ? (uint32_t)v : 2u;
-    }();
-    return n;
+    const char* e = getenv(name);
+    if (!e || !*e) return fallback;
+    const int v = atoi(e);
+    return (v >= lo && v <= hi) ? v : fallback;
 }
+
+// Depth of the tile ring and block rows per tile.  GOOFY_B200_TMA_STAGES (2..8) and GOOFY_B200_TMA_ROWS (1, 2, 4)
+// override them for experiments.
+uint32_t tma_stages() { static const uint32_t n = (uint32_t)env_int("GOOFY_B200_TMA_STAGES", 2, gb::kTmaMaxStages, 3); return n; }
+uint32_t tma_rows() { static const uint32_t n = (uint32_t)env_int("GOOFY_B200_TMA_ROWS", 1, 4, 4); return n == 3u ? 4u : n; }
+
 gb::FastDiv make_fastdiv(uint32_t d)
 {
     gb::FastDiv f;
@@ -173,69 +211,104 @@ gb::FastDiv make_fastdiv(uint32_t d)
     return f;
 }
 
-// Shapes the tile kernel's index arithmetic covers (FastDiv ranges, tensor-map limits).
+constexpr uint64_t kTmaMaxTiles = (1ull << 24) - 1u;   // FastDiv range
+
+// Shapes the tile kernel's index arithmetic covers (FastDiv ranges, tensor-map limits).  Batches with more warp tiles
+// than FastDiv covers are cut into several launches by launch_tma, so only one image has to fit.
 bool tma_eligible(uint32_t bw, uint32_t bh, uint32_t stride, uint64_t srcPitch, uint32_t nImages)
 {
-    const uint64_t tilesX = (bw + gb::kTmaThreads - 1u) / gb::kTmaThreads;
-    const uint64_t nTiles = tilesX * bh * nImages;
-    if (bh > 65536u || tilesX > 65536u || nTiles >= (1ull << 24)) return false;
+    const uint64_t tilesX = (bw + gb::kTmaTileBlocksX - 1u) / gb::kTmaTileBlocksX;
+    if (bh > 65536u || tilesX > 65536u || tilesX * bh > kTmaMaxTiles) return false;
     if (nImages > 1u && (srcPitch % 16u != 0u || srcPitch >= (1ull << 40))) return false;
     if ((uint64_t)stride * bh * 4u >= (1ull << 40)) return false;
     return tensor_map_encoder() != nullptr;
+}
+
+template <int MODE, int RB>
+int launch_tma_r(void* dst, void* dst2, const void* src, uint32_t width, uint32_t height, uint32_t stride, uint64_t srcPitch,
+                 uint64_t dstPitch, uint32_t nImages, cudaStream_t stream, int dev)
+{
+    constexpr int kLog = RB == 1 ? 0 : RB == 2 ? 1 : 2;
+    const uint32_t nStages = tma_stages();
+    const int smemBytes = (int)nStages * RB * gb::kTmaBlockRowBytes;
+    int smCount = 0, ctasPerSm = 0;
+    {
+        std::lock_guard<std::mutex> g(g_devInfoMutex);
+        DeviceInfo& di = g_devInfo[dev];
+        if (di.smCount == 0) GB_CUDA(cudaDeviceGetAttribute(&di.smCount, cudaDevAttrMultiProcessorCount, dev));
+        if (di.tmaCtasPerSm[MODE][kLog] == 0 || di.tmaSmemBytes[MODE][kLog] != smemBytes) {
+            GB_CUDA(cudaFuncSetAttribute(gb::encode_tma_kernel<MODE, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+            int n = 0;
+            GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gb::encode_tma_kernel<MODE, RB>, gb::tma_threads(RB), smemBytes));
+            di.tmaCtasPerSm[MODE][kLog] = n > 0 ? n : 1;
+            di.tmaSmemBytes[MODE][kLog] = smemBytes;
+        }
+        smCount = di.smCount;
+        ctasPerSm = di.tmaCtasPerSm[MODE][kLog];
+    }
+    static const int promo = env_int("GOOFY_B200_TMA_L2PROMO", 0, 3, 3);
+    static const uint32_t hint = (uint32_t)env_int("GOOFY_B200_TMA_HINT", 0, 1, 0);   // evict-first costs 4 % (round 1)
+    // Persistent grid: tiles are dealt round-robin to the resident CTAs, whose rings keep them out of lock-step.
+    // GOOFY_B200_TMA_GRID_MULT > 1 launches that many times more CTAs (each then walks fewer tiles).
+    static const uint32_t gridMult = (uint32_t)env_int("GOOFY_B200_TMA_GRID_MULT", 1, 64, 1);
+
+    const uint32_t bw = width / 4u, bh = height / 4u;
+    const uint32_t tilesX = (bw + gb::kTmaTileBlocksX - 1u) / gb::kTmaTileBlocksX, groups = (bh + (uint32_t)RB - 1u) / (uint32_t)RB;
+    const uint64_t tilesPerImage = (uint64_t)tilesX * groups;
+    const uint32_t imagesPerLaunch = (uint32_t)std::min<uint64_t>(nImages, kTmaMaxTiles / tilesPerImage);
+    for (uint32_t img0 = 0; img0 < nImages; img0 += imagesPerLaunch) {
+        const uint32_t n = std::min(imagesPerLaunch, nImages - img0);
+        const uint8_t* s0 = (const uint8_t*)src + (uint64_t)img0 * srcPitch;
+        CUtensorMap map;
+        const cuuint64_t dims[3] = {width, height, n};
+        const cuuint64_t strides[2] = {stride, n > 1u ? srcPitch : (cuuint64_t)stride * height};
+        const cuuint32_t box[3] = {(cuuint32_t)gb::kTmaBoxPixels, (cuuint32_t)(4 * RB), 1u};
+        const cuuint32_t elemStrides[3] = {1u, 1u, 1u};
+        const CUresult r = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(s0), dims, strides, box,
+                                                elemStrides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return GOOFY_B200_E_ARGS;
+        gb::TmaParams P;
+        P.dst = (uint8_t*)dst + (uint64_t)img0 * dstPitch;
+        P.dst2 = dst2 ? (uint8_t*)dst2 + (uint64_t)img0 * dstPitch : nullptr;
+        P.dstPitch = dstPitch;
+        P.bw = bw;
+        P.bh = bh;
+        P.nTiles = (uint32_t)(tilesPerImage * n);
+        P.nStages = nStages;
+        P.evictFirst = hint;
+        P.tilesX = make_fastdiv(tilesX);
+        P.groups = make_fastdiv(groups);
+        uint32_t grid = (uint32_t)smCount * (uint32_t)ctasPerSm * gridMult;
+        if (grid > P.nTiles) grid = P.nTiles;
+
+        static const bool pdl = env_int("GOOFY_B200_PDL", 0, 1, 1) != 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid, 1, 1);
+        cfg.blockDim = dim3(gb::tma_threads(RB), 1, 1);
+        cfg.dynamicSmemBytes = (size_t)smemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, gb::encode_tma_kernel<MODE, RB>, map, P);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    return GOOFY_B200_OK;
 }
 
 template <int MODE>
 int launch_tma(void* dst, void* dst2, const void* src, uint32_t width, uint32_t height, uint32_t stride, uint64_t srcPitch,
                uint64_t dstPitch, uint32_t nImages, cudaStream_t stream, int dev)
 {
-    CUtensorMap map;
-    const cuuint64_t dims[3] = {width, height, nImages};
-    const cuuint64_t strides[2] = {stride, nImages > 1u ? srcPitch : (cuuint64_t)stride * height};
-    const cuuint32_t box[3] = {(cuuint32_t)gb::kTmaBoxPixels, 4u, 1u};
-    const cuuint32_t elemStrides[3] = {1u, 1u, 1u};
-    static const int promo = []() { const char* e = getenv("GOOFY_B200_TMA_L2PROMO"); const int v = e ? atoi(e) : 3; return (v >= 0 && v <= 3) ? v : 3; }();
-    const CUresult r = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(src), dims, strides, box,
-                                            elemStrides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                            (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return GOOFY_B200_E_ARGS;
-
-    const uint32_t nStages = tma_stages();
-    const int smemBytes = (int)nStages * gb::kTmaStageBytes;
-    int smCount = 0, ctasPerSm = 0;
-    {
-        std::lock_guard<std::mutex> g(g_devInfoMutex);
-        DeviceInfo& di = g_devInfo[dev];
-        if (di.smCount == 0) GB_CUDA(cudaDeviceGetAttribute(&di.smCount, cudaDevAttrMultiProcessorCount, dev));
-        if (di.tmaCtasPerSm[MODE] == 0) {
-            GB_CUDA(cudaFuncSetAttribute(gb::encode_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-            int n = 0;
-            GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gb::encode_tma_kernel<MODE>, gb::kTmaThreads, smemBytes));
-            di.tmaCtasPerSm[MODE] = n > 0 ? n : 1;
-        }
-        smCount = di.smCount;
-        ctasPerSm = di.tmaCtasPerSm[MODE];
+    switch (tma_rows()) {
+        case 1u: return launch_tma_r<MODE, 1>(dst, dst2, src, width, height, stride, srcPitch, dstPitch, nImages, stream, dev);
+        case 2u: return launch_tma_r<MODE, 2>(dst, dst2, src, width, height, stride, srcPitch, dstPitch, nImages, stream, dev);
+        default: return launch_tma_r<MODE, 4>(dst, dst2, src, width, height, stride, srcPitch, dstPitch, nImages, stream, dev);
     }
-    gb::TmaParams P;
-    P.dst = (uint8_t*)dst;
-    P.dst2 = (uint8_t*)dst2;
-    P.dstPitch = dstPitch;
-    P.bw = width / 4u;
-    P.bh = height / 4u;
-    const uint32_t tilesX = (P.bw + gb::kTmaThreads - 1u) / gb::kTmaThreads;
-    P.nTiles = tilesX * P.bh * nImages;
-    P.nStages = nStages;
-    static const uint32_t hint = []() { const char* e = getenv("GOOFY_B200_TMA_HINT"); return (e && e[0] == '1') ? 1u : 0u; }();
-    P.evictFirst = hint;  // off by default: the evict-first policy costs 4 % (6543 vs 6815 GB/s, DXT1)
-    P.tilesX = make_fastdiv(tilesX);
-    P.rows = make_fastdiv(P.bh);
-    // CTAs walk a few tiles each: a multiple of what is resident at once (fully persistent CTAs run in
-    // lock-step and are slower, as with the row-walking kernels), never more than there are tiles
-    static const uint32_t gridMult = []() { const char* e = getenv("GOOFY_B200_TMA_GRID_MULT"); const int v = e ? atoi(e) : 8; return v > 0 ? (uint32_t)v : 8u; }();
-    uint32_t grid = (uint32_t)smCount * (uint32_t)ctasPerSm * gridMult;
-    if (grid > P.nTiles) grid = P.nTiles;
-    gb::encode_tma_kernel<MODE><<<grid, gb::kTmaThreads, smemBytes, stream>>>(map, P);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cuda_rc(cudaGetLastError());
 }
 
 // Which load layer serves a uniform launch.  AUTO: see DESIGN.md section 3 ("load path policy").
@@ -246,6 +319,14 @@ bool choose_tma(uint32_t bw, uint32_t bh, uint32_t stride, uint64_t srcPitch, ui
     if (!tma_eligible(bw, bh, stride, srcPitch, nImages)) return false;
     if (path == GOOFY_B200_LOAD_TMA) return true;
     return false;
+}
+
+// Images of a batch must not overlap: a pitch of 0 (or any pitch smaller than one image / one result) would make
+// every image read the same pixels or overwrite the same blocks while the call still reports success.
+bool pitches_cover_images(uint32_t width, uint32_t height, uint32_t stride, uint64_t srcPitch, uint64_t dstPitch)
+{
+    const uint64_t imageSpan = (uint64_t)(height - 1u) * stride + (uint64_t)width * 4u;
+    return srcPitch >= imageSpan && dstPitch >= (uint64_t)width * height / 2u;
 }
 
 int encode_uniform(int mode, void* dst, void* dst2, const void* src, uint32_t width, uint32_t height, uint32_t stride,
@@ -261,6 +342,7 @@ int encode_uniform(int mode, void* dst, void* dst2, const void* src, uint32_t wi
         if (rc != GOOFY_B200_OK) return rc;
     }
     if (nImages > 1u && ((srcPitch & 15u) != 0u || (dstPitch & 7u) != 0u)) return GOOFY_B200_E_ALIGN;
+    if (nImages > 1u && !pitches_cover_images(width, height, stride, srcPitch, dstPitch)) return GOOFY_B200_E_ARGS;
     int dev = -1;
     rc = ensure_device_ready(&dev);
     if (rc != GOOFY_B200_OK) return rc;
@@ -274,7 +356,7 @@ int encode_uniform(int mode, void* dst, void* dst2, const void* src, uint32_t wi
         }
     }
 
-    gb::EncodeParams P;
+    gb::EncodeParams P = {};
     P.src = (const uint8_t*)src;
     P.dst = (uint8_t*)dst;
     P.dst2 = (uint8_t*)dst2;
@@ -302,9 +384,10 @@ int encode_floatref(int codec, void* dst, const void* src, uint32_t width, uint3
     rc = check_pointers(src, dst);
     if (rc != GOOFY_B200_OK) return rc;
     if (nImages > 1u && ((srcPitch & 15u) != 0u || (dstPitch & 7u) != 0u)) return GOOFY_B200_E_ALIGN;
+    if (nImages > 1u && !pitches_cover_images(width, height, stride, srcPitch, dstPitch)) return GOOFY_B200_E_ARGS;
     rc = ensure_device_ready();
     if (rc != GOOFY_B200_OK) return rc;
-    gb::EncodeParams P;
+    gb::EncodeParams P = {};
     P.src = (const uint8_t*)src;
     P.dst = (uint8_t*)dst;
     P.dst2 = nullptr;
