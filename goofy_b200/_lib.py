@@ -21,6 +21,7 @@ class GoofyB200Image(C.Structure):
         ("height", C.c_uint32),
         ("stride", C.c_uint32),
         ("device", C.c_int32),
+        ("dst2", C.c_void_p),
     ]
 
 
@@ -32,6 +33,7 @@ PROTOTYPES = {
     "goofy_b200_device_count": (_int, []),
     "goofy_b200_error_string": (C.c_char_p, [_int]),
     "goofy_b200_kernel_launches": (_u64, []),
+    "goofy_b200_host_scratch_sets": (_u64, []),
     "goofy_b200_set_load_path": (_int, [_int]),
     "goofy_b200_get_load_path": (_int, []),
     "goofy_b200_compress_dxt1": (_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_uint]),
@@ -50,6 +52,7 @@ PROTOTYPES = {
     "goofy_b200_encode_batch_device": (_int, [_int, C.POINTER(GoofyB200Image), _u32, _vp]),
     "goofy_b200_encode_batch_sharded": (_int, [_int, C.POINTER(GoofyB200Image), _u32]),
     "goofy_b200_encode_sharded_host": (_int, [_int, _vp, _vp, _u32, _u32, _u32, _int]),
+    "goofy_b200_encode_dual_sharded_host": (_int, [_vp, _vp, _vp, _u32, _u32, _u32, _int]),
     "goofy_b200_strip_partition": (None, [_u32, _int, _int, C.POINTER(_u32), C.POINTER(_u32)]),
 }
 

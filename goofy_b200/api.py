@@ -22,10 +22,11 @@ from ._lib import GoofyB200Image
 
 DXT1 = 0
 ETC1 = 1
+BOTH = 2   # batch entry points: DXT1 blocks to dst, ETC1s blocks to dst2, one read of every pixel
 # bit-exact with goofyRef:: (Src/goofy_tc_reference.cpp) instead of with the SSE2 path
 DXT1_FLOATREF = 16
 ETC1_FLOATREF = 17
-CODEC_NAMES = {DXT1: "dxt1", ETC1: "etc1", DXT1_FLOATREF: "dxt1_floatref", ETC1_FLOATREF: "etc1_floatref"}
+CODEC_NAMES = {DXT1: "dxt1", ETC1: "etc1", BOTH: "dxt1+etc1", DXT1_FLOATREF: "dxt1_floatref", ETC1_FLOATREF: "etc1_floatref"}
 
 
 class GoofyError(RuntimeError):
@@ -44,6 +45,11 @@ def device_count() -> int:
 
 def kernel_launches() -> int:
     return int(_lib.load().goofy_b200_kernel_launches())
+
+
+def host_scratch_sets() -> int:
+    """Scratch sets of the host paths created so far (they are pooled and leased per thread)."""
+    return int(_lib.load().goofy_b200_host_scratch_sets())
 
 
 LOAD_AUTO, LOAD_DIRECT, LOAD_TMA, LOAD_ONESHOT, LOAD_ASYNC = 0, 1, 2, 3, 4
@@ -143,12 +149,15 @@ def encode_dual_host(result_dxt1, result_etc1, input, width: int, height: int, s
 
 
 def encode_host_batch(codec: int, images) -> int:
-    """images: iterable of (input, result, width, height, stride) with HOST buffers (numpy uint8 arrays or pinned
-    torch tensors).  One pipeline for all of them: copies and kernels of neighbouring images overlap."""
+    """images: iterable of (input, result, width, height, stride[, result2]) with HOST buffers (numpy uint8 arrays or pinned
+    torch tensors); codec BOTH needs result2 (the ETC1s blocks).  One pipeline for all of them: copies and kernels of
+    neighbouring images overlap."""
     items = list(images)
     arr = (GoofyB200Image * max(len(items), 1))()
-    for i, (src, dst, w, h, stride) in enumerate(items):
-        arr[i] = GoofyB200Image(_host_ptr(src, False), _host_ptr(dst, True), w, h, stride, -1)
+    for i, it in enumerate(items):
+        src, dst, w, h, stride = it[:5]
+        dst2 = it[5] if len(it) > 5 else None
+        arr[i] = GoofyB200Image(_host_ptr(src, False), _host_ptr(dst, True), w, h, stride, -1, _host_ptr(dst2, True))
     return int(_lib.load().goofy_b200_encode_host_batch(codec, arr, len(items)))
 
 
@@ -156,6 +165,12 @@ def encode_sharded_host(codec: int, result, input, width: int, height: int, stri
     """One host image, horizontal strips of whole block rows, strip g on GPU g (no collectives)."""
     return int(_lib.load().goofy_b200_encode_sharded_host(codec, _host_ptr(result, True), _host_ptr(input, False),
                                                           width, height, stride, n_gpus))
+
+
+def encode_dual_sharded_host(result_dxt1, result_etc1, input, width: int, height: int, stride: int, n_gpus: int = 0) -> int:
+    """The same partition, both codecs from one upload of every strip."""
+    return int(_lib.load().goofy_b200_encode_dual_sharded_host(_host_ptr(result_dxt1, True), _host_ptr(result_etc1, True),
+                                                               _host_ptr(input, False), width, height, stride, n_gpus))
 
 
 # ------------------------------------------------------------------ device-resident API
@@ -206,13 +221,14 @@ def psnr_rgb768(sse_rgb, pixels: int) -> float:
 
 
 def make_descriptors(images: Iterable[Sequence]) -> C.Array:
-    """images: iterable of (d_src, d_dst, width, height, stride[, device]) -> GoofyB200Image[n]."""
+    """images: iterable of (d_src, d_dst, width, height, stride[, device[, d_dst2]]) -> GoofyB200Image[n]."""
     items = list(images)
     arr = (GoofyB200Image * len(items))()
     for i, it in enumerate(items):
         src, dst, w, h, stride = it[:5]
         dev = it[5] if len(it) > 5 else -1
-        arr[i] = GoofyB200Image(_dev_ptr(src), _dev_ptr(dst), w, h, stride, dev)
+        dst2 = it[6] if len(it) > 6 else None
+        arr[i] = GoofyB200Image(_dev_ptr(src), _dev_ptr(dst), w, h, stride, dev, _dev_ptr(dst2))
     return arr
 
 

@@ -3,6 +3,7 @@
 // Thin by design: the entry points only validate and dispatch.  The host side is split into
 //   host_common.cuh    error codes, per-device set-up, the reference's argument checks
 //   host_launch.cuh    load-layer policy and kernel launches (device-resident entry points)
+//   host_resources.cuh per-thread scratch of the host paths, leased from a process-wide pool
 //   host_pipeline.cuh  the drop-in host-pointer path (strip pipeline, pinned staging)
 //   host_batch.cuh     ragged batches and the multi-GPU shard scheduler
 // and everything is compiled as ONE translation unit (the kernels' __device__ tables live in it).
@@ -42,6 +43,8 @@ int goofy_b200_abi_version(void) { return GOOFY_B200_ABI_VERSION; }
 int goofy_b200_device_count(void) { return device_count(); }
 
 uint64_t goofy_b200_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+uint64_t goofy_b200_host_scratch_sets(void) { return ResourcePool::get().created(); }
 
 int goofy_b200_set_load_path(int path)
 {
@@ -242,7 +245,7 @@ int goofy_b200_encode_batch_device(int codec, const GoofyB200Image* descs, uint3
 
 int goofy_b200_encode_batch_sharded(int codec, const GoofyB200Image* descs, uint32_t n_images)
 {
-    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
+    if (codec != GOOFY_B200_BOTH && !is_codec(codec)) return GOOFY_B200_E_CODEC;
     if (n_images == 0u) return GOOFY_B200_OK;
     if (!descs) return GOOFY_B200_E_NULL;
     const int nDev = device_count();
@@ -286,10 +289,10 @@ void goofy_b200_strip_partition(uint32_t height, int n_shards, int shard, uint32
     if (block_row_count) *block_row_count = count;
 }
 
-int goofy_b200_encode_sharded_host(int codec, void* result, const void* input, uint32_t width, uint32_t height,
-                                   uint32_t stride, int n_gpus)
+// One host image in strips of whole block rows, strip g on device g through the host path (result2 != null: both codecs).
+static int sharded_host(int codec, void* result, void* result2, const void* input, uint32_t width, uint32_t height, uint32_t stride,
+                        int n_gpus)
 {
-    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
     int rc = check_shape(width, height, stride);
     if (rc != GOOFY_B200_OK) return rc;
     if (width == 0u || height == 0u) return GOOFY_B200_OK;
@@ -305,9 +308,13 @@ int goofy_b200_encode_sharded_host(int codec, void* result, const void* input, u
         uint32_t first = 0, count = 0;
         goofy_b200_strip_partition(height, n_gpus, g, &first, &count);
         if (count == 0u) continue;
-        uint8_t* out = (uint8_t*)result + (size_t)first * (width / 4u) * 8u;
+        const size_t outOffset = (size_t)first * (width / 4u) * 8u;
+        uint8_t* out = (uint8_t*)result + outOffset;
+        uint8_t* out2 = result2 ? (uint8_t*)result2 + outOffset : nullptr;
         const uint8_t* in = (const uint8_t*)input + (size_t)first * 4u * stride;
-        worker_for(g)->submit([=]() { return encode_host(codec, out, in, width, count * 4u, stride); });
+        worker_for(g)->submit([=]() {
+            return out2 ? encode_dual_host(out, out2, in, width, count * 4u, stride) : encode_host(codec, out, in, width, count * 4u, stride);
+        });
         used.push_back(g);
     }
     for (int g : used) {
@@ -315,6 +322,20 @@ int goofy_b200_encode_sharded_host(int codec, void* result, const void* input, u
         if (r != GOOFY_B200_OK && rc == GOOFY_B200_OK) rc = r;
     }
     return rc;
+}
+
+int goofy_b200_encode_sharded_host(int codec, void* result, const void* input, uint32_t width, uint32_t height,
+                                   uint32_t stride, int n_gpus)
+{
+    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
+    return sharded_host(codec, result, nullptr, input, width, height, stride, n_gpus);
+}
+
+int goofy_b200_encode_dual_sharded_host(void* result_dxt1, void* result_etc1, const void* input, uint32_t width, uint32_t height,
+                                        uint32_t stride, int n_gpus)
+{
+    if (width != 0u && height != 0u && width % 16u == 0u && height % 4u == 0u && !result_etc1) return GOOFY_B200_E_NULL;
+    return sharded_host(GOOFY_B200_DXT1, result_dxt1, result_etc1, input, width, height, stride, n_gpus);
 }
 
 }  // extern "C"

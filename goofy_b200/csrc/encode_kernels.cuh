@@ -57,6 +57,7 @@ struct EncodeParams {
     uint32_t stride;     // bytes between pixel rows
     uint32_t by0;        // first block row handled by this launch (grid.y chunking)
     uint32_t firstWave;  // CTAs (in launch order) that warm L2 with their first tile before griddepcontrol.wait; 0 = none
+    uint32_t prefetchNext;  // row-walking kernel: warm L2 with the thread's NEXT block row while encoding this one (short launches)
     uint64_t srcPitch;   // bytes between images
     uint64_t dstPitch;
 };
@@ -148,13 +149,35 @@ __device__ __forceinline__ void encode_and_store(const uint4& r0, const uint4& r
     }
 }
 
+// The same for either flavour: FLAVOUR 0 = SSE2-exact (goofy::), 1 = float-reference-exact (goofyRef::, single codecs only).
+template <int MODE, int FLAVOUR>
+__device__ __forceinline__ void encode_and_store_flavour(const uint4& r0, const uint4& r1, const uint4& r2, const uint4& r3,
+                                                         const uint32_t* lut, uint8_t* dst, uint8_t* dst2)
+{
+    if (FLAVOUR == 0) {
+        encode_and_store<MODE>(r0, r1, r2, r3, lut, dst, dst2);
+    } else {
+        const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
+                                r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+        // minimum brightness range: 8 for DXT1 (Src/goofy_tc_reference.cpp:667), 16 for ETC1S (:766), times 4
+        const RefFront f = analyse_ref(p, MODE == kDxt1 ? 32u : 64u);
+        uint32_t w0, w1;
+        if (MODE == kDxt1) encode_dxt1_ref(p, f, w0, w1);
+        else encode_etc1_ref(p, f, lut, w0, w1);
+        store_block(dst, w0, w1);
+    }
+}
+
 // Resident CTAs per SM: 8 (32 registers) for DXT1, 6 (40 registers) for ETC1s and dual-output (ctas_per_sm).
 // WIDE = false: every byte offset inside one image fits 32 bits (the launcher checks), which
 // keeps the address arithmetic to a handful of 32-bit ops; WIDE = true is the same kernel with
 // 64-bit offsets for images of 4 GiB and more.
 // PITCHED = true adds blockIdx.z * pitch for batches whose images are not back to back (batches
 // that ARE back to back are launched as one tall image, so the common case pays nothing).
-template <int MODE, bool WIDE, bool PITCHED>
+// SHORT = the instantiation for short launches: its first wave of CTAs warms L2 before griddepcontrol.wait (prefetch_l2).
+// Long launches run the instantiation without that code: two dozen instructions per block are worth 1-5 % to the
+// kernels that sit near their issue limit when the box is power-capped.
+template <int MODE, bool WIDE, bool PITCHED, bool SHORT>
 __global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) encode_direct_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
@@ -177,7 +200,7 @@ __global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) enco
         dst += (uint64_t)blockIdx.z * P.dstPitch;
         if (MODE == kDual) dst2 += (uint64_t)blockIdx.z * P.dstPitch;
     }
-    if (P.firstWave != 0u) {
+    if (SHORT && P.firstWave != 0u) {
         const uint32_t cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         if (cta < P.firstWave && live && (threadIdx.x & 7u) == 0u) {   // eight neighbouring threads share a 128-byte line
             prefetch_l2(src + o0);
@@ -202,30 +225,32 @@ __global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) enco
 // are resident at once).  PITCHED: blockIdx.z picks the image of a batch laid out at fixed pitches.  The per-thread set-up
 // (indices, control table, constants) is paid once and each further block costs only the
 // pointer bumps -- about 25 fewer instructions per block than one-shot CTAs.
-template <int MODE, bool WIDE, bool PITCHED>
-__global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) encode_rows_kernel(const EncodeParams P0)
+template <int MODE, bool WIDE, bool PITCHED, bool SHORT>
+__global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) encode_rows_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     pdl_launch_dependents();
     if (MODE != kDxt1) stage_control_lut<false, GB_TPB>(lut, threadIdx.y * blockDim.x + threadIdx.x);
-    EncodeParams P = P0;
+    const uint8_t* src = P.src;
+    uint8_t* dst = P.dst;
+    uint8_t* dst2 = P.dst2;
     if (PITCHED) {   // grid.z = image of a batch laid out at fixed pitches
-        P.src += (uint64_t)blockIdx.z * P.srcPitch;
-        P.dst += (uint64_t)blockIdx.z * P.dstPitch;
-        if (MODE == kDual) P.dst2 += (uint64_t)blockIdx.z * P.dstPitch;
+        src += (uint64_t)blockIdx.z * P.srcPitch;
+        dst += (uint64_t)blockIdx.z * P.dstPitch;
+        if (MODE == kDual) dst2 += (uint64_t)blockIdx.z * P.dstPitch;
     }
     const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t by = blockIdx.y * blockDim.y + threadIdx.y;
     const bool live = bx < P.bw && by < P.bh;
     typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type off_t;
-    if (P.firstWave != 0u) {
+    if (SHORT && P.firstWave != 0u) {
         const uint32_t cta = blockIdx.x + gridDim.x * (blockIdx.y + (PITCHED ? gridDim.y * blockIdx.z : 0u));
         if (cta < P.firstWave && live && (threadIdx.x & 7u) == 0u) {
             const off_t o0 = (off_t)by * ((off_t)4u * P.stride) + (off_t)(bx * 16u);
-            prefetch_l2(P.src + o0);
-            prefetch_l2(P.src + o0 + P.stride);
-            prefetch_l2(P.src + o0 + 2u * (off_t)P.stride);
-            prefetch_l2(P.src + o0 + 3u * (off_t)P.stride);
+            prefetch_l2(src + o0);
+            prefetch_l2(src + o0 + P.stride);
+            prefetch_l2(src + o0 + 2u * (off_t)P.stride);
+            prefetch_l2(src + o0 + 3u * (off_t)P.stride);
         }
     }
     pdl_wait();
@@ -239,12 +264,21 @@ __global__ void __launch_bounds__(GB_TPB, ctas_per_sm(MODE) * 256 / GB_TPB) enco
     for (; by < P.bh; by += rowStep) {
         const off_t o0 = (off_t)by * ((off_t)4u * P.stride) + (off_t)(bx * 16u);
         const off_t o1 = o0 + P.stride, o2 = o1 + P.stride, o3 = o2 + P.stride;
-        const uint4 r0 = load_row(P.src + o0);
-        const uint4 r1 = load_row(P.src + o1);
-        const uint4 r2 = load_row(P.src + o2);
-        const uint4 r3 = load_row(P.src + o3);
+        if (SHORT && P.prefetchNext != 0u && (threadIdx.x & 7u) == 0u && by + rowStep < P.bh) {
+            // a short launch never reaches the steady state in which the warps of an SM sit in different phases: its
+            // CTAs load together and encode together, so DRAM idles while they encode unless somebody keeps it busy
+            const off_t n0 = o0 + (off_t)rowStep * ((off_t)4u * P.stride);
+            prefetch_l2(src + n0);
+            prefetch_l2(src + n0 + P.stride);
+            prefetch_l2(src + n0 + 2u * (off_t)P.stride);
+            prefetch_l2(src + n0 + 3u * (off_t)P.stride);
+        }
+        const uint4 r0 = load_row(src + o0);
+        const uint4 r1 = load_row(src + o1);
+        const uint4 r2 = load_row(src + o2);
+        const uint4 r3 = load_row(src + o3);
         const off_t o = ((off_t)by * P.bw + bx) * 8u;
-        encode_and_store<MODE>(r0, r1, r2, r3, lut, P.dst + o, MODE == kDual ? P.dst2 + o : nullptr);
+        encode_and_store<MODE>(r0, r1, r2, r3, lut, dst + o, MODE == kDual ? dst2 + o : nullptr);
     }
 }
 
@@ -396,6 +430,7 @@ __global__ void __launch_bounds__(256, 6) encode_relaxed_kernel(const uint8_t* _
 struct BatchImage {
     const uint8_t* src;
     uint8_t* dst;
+    uint8_t* dst2;    // dual-output batches: the ETC1s blocks
     uint32_t bw, bh;
     uint32_t stride;
     uint32_t tilesX;  // CTAs per block row
@@ -404,7 +439,7 @@ struct BatchImage {
 constexpr int kBatchTileX = 64;    // blocks per CTA in x
 constexpr int kBatchTileY = 4;     // block rows per pass (threads in y)
 constexpr int kBatchPasses = 4;    // passes per CTA
-constexpr int kBatchInline = 48;   // largest batch passed as kernel parameters
+constexpr int kBatchInline = 40;   // largest batch passed as kernel parameters (40 x 44 bytes: well inside the 4 KiB limit)
 
 struct BatchTableGlobal {
     const BatchImage* images;
@@ -419,13 +454,13 @@ struct BatchTableInline {
     __device__ __forceinline__ BatchImage image(uint32_t i) const { return images[i]; }
 };
 
-template <int MODE, typename TABLE>
+template <int MODE, int FLAVOUR, typename TABLE>
 __global__ void __launch_bounds__(kBatchTileX* kBatchTileY, ctas_per_sm(MODE))
     encode_batch_kernel(const __grid_constant__ TABLE table, uint32_t nImages)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
     if (MODE != kDxt1) {
-        stage_control_lut<false, kBatchTileX * kBatchTileY>(lut, threadIdx.y * kBatchTileX + threadIdx.x);
+        stage_control_lut<FLAVOUR != 0, kBatchTileX * kBatchTileY>(lut, threadIdx.y * kBatchTileX + threadIdx.x);
         __syncthreads();
     }
     // largest i with start(i) <= blockIdx.x
@@ -448,7 +483,8 @@ __global__ void __launch_bounds__(kBatchTileX* kBatchTileY, ctas_per_sm(MODE))
         const uint4 r1 = load_row(s + im.stride);
         const uint4 r2 = load_row(s + 2ull * im.stride);
         const uint4 r3 = load_row(s + 3ull * im.stride);
-        encode_and_store<MODE>(r0, r1, r2, r3, lut, im.dst + ((uint64_t)by * im.bw + bx) * 8u, nullptr);
+        const uint64_t o = ((uint64_t)by * im.bw + bx) * 8u;
+        encode_and_store_flavour<MODE, FLAVOUR>(r0, r1, r2, r3, lut, im.dst + o, MODE == kDual ? im.dst2 + o : nullptr);
     }
 }
 

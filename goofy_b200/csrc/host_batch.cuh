@@ -6,27 +6,32 @@
 namespace {
 
 // ---------------------------------------------------------------- ragged batch
-template <int MODE, typename TABLE>
+template <int MODE, int FLAVOUR, typename TABLE>
 int launch_batch(const TABLE& table, uint32_t n, uint32_t totalCtas, cudaStream_t stream)
 {
-    gb::encode_batch_kernel<MODE, TABLE><<<totalCtas, dim3(gb::kBatchTileX, gb::kBatchTileY, 1), 0, stream>>>(table, n);
+    gb::encode_batch_kernel<MODE, FLAVOUR, TABLE><<<totalCtas, dim3(gb::kBatchTileX, gb::kBatchTileY, 1), 0, stream>>>(table, n);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cuda_rc(cudaGetLastError());
 }
 
-// Descriptor tables live in a small per-thread device arena that is recycled in stream order.
-struct BatchArena {
-    void* dev = nullptr;
-    void* host = nullptr;  // pinned
-    size_t cap = 0;
-    int device = -1;
-    cudaEvent_t done = nullptr;
-};
-thread_local BatchArena t_arena;
+// codec: DXT1, ETC1, BOTH, or a float-reference flavour
+template <typename TABLE>
+int launch_batch_codec(int codec, const TABLE& table, uint32_t n, uint32_t totalCtas, cudaStream_t stream)
+{
+    switch (codec) {
+        case GOOFY_B200_DXT1: return launch_batch<gb::kDxt1, 0>(table, n, totalCtas, stream);
+        case GOOFY_B200_ETC1: return launch_batch<gb::kEtc1, 0>(table, n, totalCtas, stream);
+        case GOOFY_B200_BOTH: return launch_batch<gb::kDual, 0>(table, n, totalCtas, stream);
+        case GOOFY_B200_DXT1_FLOATREF: return launch_batch<gb::kDxt1, 1>(table, n, totalCtas, stream);
+        case GOOFY_B200_ETC1_FLOATREF: return launch_batch<gb::kEtc1, 1>(table, n, totalCtas, stream);
+        default: return GOOFY_B200_E_CODEC;
+    }
+}
 
 int encode_batch_current_device(int codec, const GoofyB200Image* descs, const uint32_t* order, uint32_t n, cudaStream_t stream)
 {
-    if (codec != GOOFY_B200_DXT1 && codec != GOOFY_B200_ETC1) return GOOFY_B200_E_CODEC;
+    const bool both = codec == GOOFY_B200_BOTH;
+    if (!both && !is_codec(codec)) return GOOFY_B200_E_CODEC;
     if (n == 0u) return GOOFY_B200_OK;
     if (!descs) return GOOFY_B200_E_NULL;
     int dev = -1;
@@ -40,14 +45,19 @@ int encode_batch_current_device(int codec, const GoofyB200Image* descs, const ui
     uint64_t total = 0;
     for (uint32_t k = 0; k < n; ++k) {
         const GoofyB200Image& d = descs[order ? order[k] : k];
-        rc = check_shape(d.width, d.height, d.stride);
+        rc = is_floatref(codec) ? check_shape_floatref(d.width, d.height, d.stride) : check_shape(d.width, d.height, d.stride);
         if (rc != GOOFY_B200_OK) return rc;
         if (d.width == 0u || d.height == 0u) continue;
         rc = check_pointers(d.src, d.dst);
         if (rc != GOOFY_B200_OK) return rc;
+        if (both) {
+            rc = check_pointers(d.src, d.dst2);
+            if (rc != GOOFY_B200_OK) return rc;
+        }
         gb::BatchImage im;
         im.src = (const uint8_t*)d.src;
         im.dst = (uint8_t*)d.dst;
+        im.dst2 = both ? (uint8_t*)d.dst2 : nullptr;
         im.bw = d.width / 4u;
         im.bh = d.height / 4u;
         im.stride = d.stride;
@@ -65,36 +75,21 @@ int encode_batch_current_device(int codec, const GoofyB200Image* descs, const ui
         std::memset(&T, 0, sizeof(T));
         std::memcpy(T.images, images.data(), (size_t)m * sizeof(gb::BatchImage));
         std::memcpy(T.ctaStart, start.data(), (size_t)m * sizeof(uint32_t));
-        return codec == GOOFY_B200_DXT1 ? launch_batch<gb::kDxt1>(T, m, (uint32_t)total, stream)
-                                        : launch_batch<gb::kEtc1>(T, m, (uint32_t)total, stream);
+        return launch_batch_codec(codec, T, m, (uint32_t)total, stream);
     }
     const size_t bytesImages = (size_t)m * sizeof(gb::BatchImage);
     const size_t bytes = bytesImages + (size_t)m * sizeof(uint32_t);
 
-    BatchArena& A = t_arena;
-    if (A.device != dev || bytes > A.cap) {
-        if (A.done) { cudaEventSynchronize(A.done); }
-        if (A.dev) cudaFree(A.dev);
-        if (A.host) cudaFreeHost(A.host);
-        A.dev = A.host = nullptr;
-        A.cap = 0;
-        size_t cap = bytes < (1u << 16) ? (1u << 16) : bytes * 2u;
-        GB_CUDA(cudaMalloc(&A.dev, cap));
-        GB_CUDA(cudaHostAlloc(&A.host, cap, cudaHostAllocDefault));
-        if (!A.done) GB_CUDA(cudaEventCreateWithFlags(&A.done, cudaEventDisableTiming));
-        A.cap = cap;
-        A.device = dev;
-    } else if (A.done) {
-        GB_CUDA(cudaEventSynchronize(A.done));  // previous batch has consumed the table
-    }
+    BatchArena& A = thread_resources(dev).arena;
+    rc = A.prepare(dev, bytes);
+    if (rc != GOOFY_B200_OK) return rc;
     std::memcpy(A.host, images.data(), bytesImages);
     std::memcpy((uint8_t*)A.host + bytesImages, start.data(), (size_t)m * sizeof(uint32_t));
     GB_CUDA(cudaMemcpyAsync(A.dev, A.host, bytes, cudaMemcpyHostToDevice, stream));
     gb::BatchTableGlobal T;
     T.images = (const gb::BatchImage*)A.dev;
     T.ctaStart = (const uint32_t*)((const uint8_t*)A.dev + bytesImages);
-    rc = codec == GOOFY_B200_DXT1 ? launch_batch<gb::kDxt1>(T, m, (uint32_t)total, stream)
-                                  : launch_batch<gb::kEtc1>(T, m, (uint32_t)total, stream);
+    rc = launch_batch_codec(codec, T, m, (uint32_t)total, stream);
     if (rc != GOOFY_B200_OK) return rc;
     GB_CUDA(cudaEventRecord(A.done, stream));
     return GOOFY_B200_OK;

@@ -28,9 +28,22 @@ template <int MODE, bool PITCHED>
 int launch_direct_grid(const gb::EncodeParams& Q, dim3 grid, dim3 block, cudaStream_t stream)
 {
     // 32-bit in-image offsets unless the image spans 4 GiB or more
-    if ((uint64_t)Q.bh * 4u * Q.stride + (uint64_t)Q.bw * 16u < 0xFFFFFFFFull)
-        return launch_encode(gb::encode_direct_kernel<MODE, false, PITCHED>, grid, block, stream, Q);
-    return launch_encode(gb::encode_direct_kernel<MODE, true, PITCHED>, grid, block, stream, Q);
+    const bool narrow = (uint64_t)Q.bh * 4u * Q.stride + (uint64_t)Q.bw * 16u < 0xFFFFFFFFull;
+    if (Q.firstWave != 0u)   // short launch: the instantiation with the L2 warm-up
+        return narrow ? launch_encode(gb::encode_direct_kernel<MODE, false, PITCHED, true>, grid, block, stream, Q)
+                      : launch_encode(gb::encode_direct_kernel<MODE, true, PITCHED, true>, grid, block, stream, Q);
+    return narrow ? launch_encode(gb::encode_direct_kernel<MODE, false, PITCHED, false>, grid, block, stream, Q)
+                  : launch_encode(gb::encode_direct_kernel<MODE, true, PITCHED, false>, grid, block, stream, Q);
+}
+
+template <int MODE, bool PITCHED>
+int launch_rows_grid(const gb::EncodeParams& Q, dim3 grid, dim3 block, cudaStream_t stream, bool narrow)
+{
+    if (Q.firstWave != 0u || Q.prefetchNext != 0u)
+        return narrow ? launch_encode(gb::encode_rows_kernel<MODE, false, PITCHED, true>, grid, block, stream, Q)
+                      : launch_encode(gb::encode_rows_kernel<MODE, true, PITCHED, true>, grid, block, stream, Q);
+    return narrow ? launch_encode(gb::encode_rows_kernel<MODE, false, PITCHED, false>, grid, block, stream, Q)
+                  : launch_encode(gb::encode_rows_kernel<MODE, true, PITCHED, false>, grid, block, stream, Q);
 }
 
 int sm_count(int dev);
@@ -63,7 +76,11 @@ int launch_rows(const gb::EncodeParams& P, uint32_t nImages, cudaStream_t stream
     // is encoded): +2-3 % over plain loads in every A/B session since it stopped being ALU-bound (r01f sessions 3, 8, 9);
     // the single-codec kernels are faster with plain loads (ETC1s -5 % through the ring)
     const int loadPath = g_loadPath.load(std::memory_order_relaxed);
-    const bool async = nImages == 1u && (loadPath == GOOFY_B200_LOAD_ASYNC || (loadPath == GOOFY_B200_LOAD_AUTO && MODE == gb::kDual));
+    // ... on long launches: a short one (a 16384 x 2048 strip) is 9 % faster with plain loads (5576 vs 6089 GB/s, session D)
+    const uint32_t rowsPerCtaNominal = MODE == gb::kDual ? 8u : 4u;
+    const bool longLaunch = (uint64_t)gx * ((rowGroups + rowsPerCtaNominal - 1u) / rowsPerCtaNominal) >=
+                            (uint64_t)kL2PrefetchMaxWaves * (uint32_t)sms * (uint32_t)gb::ctas_per_sm(MODE);
+    const bool async = nImages == 1u && (loadPath == GOOFY_B200_LOAD_ASYNC || (loadPath == GOOFY_B200_LOAD_AUTO && MODE == gb::kDual && longLaunch));
     const uint32_t resident = async ? (uint32_t)sms * (uint32_t)GB_ASYNC_CTAS(MODE)
                                     : (uint32_t)sms * (uint32_t)gb::ctas_per_sm(MODE) * (256u / (uint32_t)GB_TPB);
     // Each CTA walks a few block rows: enough to amortise the per-thread set-up, few enough that CTAs keep
@@ -74,8 +91,18 @@ int launch_rows(const gb::EncodeParams& P, uint32_t nImages, cudaStream_t stream
     static const uint32_t rowsEnv = (uint32_t)env_int("GOOFY_B200_ROWS_PER_CTA", 1, 1 << 20, 0);
     const uint32_t rowsPerCta = rowsEnv ? rowsEnv : (MODE == gb::kDual ? 8u : 4u);
     uint32_t gy = (rowGroups + rowsPerCta - 1u) / rowsPerCta;
-    const uint32_t perImage = (resident + nImages - 1u) / nImages;   // this image's share of one resident wave
-    if (gy < perImage / gx) gy = perImage / gx;
+    // Short launches: a grid of, say, 1.4 resident waves leaves the chip half empty for the second one.  Size the grid to
+    // a whole number of waves instead (the nearest, at least one) and let the rows per CTA come out as they may.
+    static const bool quantise = env_int("GOOFY_B200_WAVE_QUANT", 0, 1, 1) != 0;
+    const uint64_t ctas0 = (uint64_t)gx * gy * nImages;
+    if (quantise && ctas0 < (uint64_t)kL2PrefetchMaxWaves * resident) {
+        uint64_t waves = (ctas0 + resident / 2u) / resident;
+        if (waves == 0u) waves = 1u;
+        gy = (uint32_t)(waves * resident / ((uint64_t)gx * nImages));
+    } else {
+        const uint32_t perImage = (resident + nImages - 1u) / nImages;   // this image's share of one resident wave
+        if (gy < perImage / gx) gy = perImage / gx;
+    }
     if (gy == 0u) gy = 1u;
     if (gy > rowGroups) gy = rowGroups;
     if (gy > 65535u) gy = 65535u;
@@ -89,16 +116,16 @@ int launch_rows(const gb::EncodeParams& P, uint32_t nImages, cudaStream_t stream
         if (Q.dst2) Q.dst2 += (uint64_t)img0 * P.dstPitch;
         const dim3 grid(gx, gy, nz);
         Q.firstWave = (!async && (uint64_t)gx * gy * nz <= (uint64_t)kL2PrefetchMaxWaves * resident) ? first_wave(resident) : 0u;
+        static const bool pfNext = env_int("GOOFY_B200_PF_NEXT", 0, 1, 1) != 0;   // +2-3 % on short ETC1s / dual launches (session E)
+        Q.prefetchNext = (pfNext && Q.firstWave != 0u) ? 1u : 0u;
         int rc;
         if (async)
             rc = narrow ? launch_encode(gb::encode_rows_async_kernel<MODE, false>, grid, block, stream, Q)
                         : launch_encode(gb::encode_rows_async_kernel<MODE, true>, grid, block, stream, Q);
         else if (nImages > 1u)
-            rc = narrow ? launch_encode(gb::encode_rows_kernel<MODE, false, true>, grid, block, stream, Q)
-                        : launch_encode(gb::encode_rows_kernel<MODE, true, true>, grid, block, stream, Q);
+            rc = launch_rows_grid<MODE, true>(Q, grid, block, stream, narrow);
         else
-            rc = narrow ? launch_encode(gb::encode_rows_kernel<MODE, false, false>, grid, block, stream, Q)
-                        : launch_encode(gb::encode_rows_kernel<MODE, true, false>, grid, block, stream, Q);
+            rc = launch_rows_grid<MODE, false>(Q, grid, block, stream, narrow);
         if (rc != GOOFY_B200_OK) return rc;
     }
     return GOOFY_B200_OK;

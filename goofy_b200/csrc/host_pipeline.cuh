@@ -1,111 +1,32 @@
 // host_pipeline.cuh -- the drop-in host-pointer path: strips of block rows pipelined H2D -> kernel -> D2H over
 // three streams; pageable buffers staged through pinned strips by a small pool of copy threads.
 #pragma once
-#include "host_launch.cuh"
+#include "host_resources.cuh"
 #include "copy_pool.h"
 
 namespace {
 
-// ---------------------------------------------------------------- host-pointer pipeline
-// The image is cut into strips of whole block rows; strip i runs H2D -> kernel -> D2H on
-// stream i % kSlots so the copies of neighbouring strips overlap each other and the kernels.
-// Device scratch is cached per host thread and device and only ever grows.
-constexpr int kSlots = 3;
-constexpr size_t kStripBytes = 16u << 20;
-
-struct HostPipe {
-    int device = -1;
-    cudaStream_t stream[kSlots] = {};
-    void* dIn[kSlots] = {};
-    void* dOut[kSlots] = {};
-    size_t capIn = 0, capOut = 0;
-    bool ready = false;
-
-    int prepare(int dev, size_t needIn, size_t needOut)
-    {
-        if (ready && dev != device) release();
-        if (!ready) {
-            for (int i = 0; i < kSlots; ++i) GB_CUDA(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
-            device = dev;
-            ready = true;
-        }
-        if (needIn > capIn) {
-            capIn = 0;  // stays 0 if an allocation below fails, so the next call starts over
-            for (int i = 0; i < kSlots; ++i) {
-                if (dIn[i]) cudaFree(dIn[i]);
-                dIn[i] = nullptr;
-                GB_CUDA(cudaMalloc(&dIn[i], needIn));
-            }
-            capIn = needIn;
-        }
-        if (needOut > capOut) {
-            capOut = 0;
-            for (int i = 0; i < kSlots; ++i) {
-                if (dOut[i]) cudaFree(dOut[i]);
-                dOut[i] = nullptr;
-                GB_CUDA(cudaMalloc(&dOut[i], needOut));
-            }
-            capOut = needOut;
-        }
-        return GOOFY_B200_OK;
-    }
-    void release()
-    {
-        for (int i = 0; i < kSlots; ++i) {
-            if (dIn[i]) cudaFree(dIn[i]);
-            if (dOut[i]) cudaFree(dOut[i]);
-            if (stream[i]) cudaStreamDestroy(stream[i]);
-            dIn[i] = dOut[i] = nullptr;
-            stream[i] = nullptr;
-        }
-        capIn = capOut = 0;
-        ready = false;
-    }
-    // No destructor on purpose: thread_local teardown can run after the CUDA runtime has
-    // shut down; the driver reclaims everything at process exit.
-};
-
-thread_local HostPipe t_pipe;
-
-// Pinned staging strips, allocated only when a pageable buffer is first seen by this thread.
-struct HostStage {
-    void* in[kSlots] = {};
-    void* out[kSlots] = {};
-    size_t capIn = 0, capOut = 0;
-    int ensure(size_t needIn, size_t needOut)
-    {
-        if (needIn > capIn) {
-            capIn = 0;
-            for (int i = 0; i < kSlots; ++i) {
-                if (in[i]) cudaFreeHost(in[i]);
-                in[i] = nullptr;
-                GB_CUDA(cudaHostAlloc(&in[i], needIn, cudaHostAllocDefault));
-            }
-            capIn = needIn;
-        }
-        if (needOut > capOut) {
-            capOut = 0;
-            for (int i = 0; i < kSlots; ++i) {
-                if (out[i]) cudaFreeHost(out[i]);
-                out[i] = nullptr;
-                GB_CUDA(cudaHostAlloc(&out[i], needOut, cudaHostAllocDefault));
-            }
-            capOut = needOut;
-        }
-        return GOOFY_B200_OK;
-    }
-};
-thread_local HostStage t_stage;
-
+// Is this host pointer ordinary (pageable) memory?  cudaPointerGetAttributes costs about a microsecond, twice per call,
+// which a 50 us call on a test-image-sized texture notices; harnesses call with the same buffers over and over
+// (the reference's: 128 times per image, Src/main.cpp:653), so the last few answers are remembered per thread.
+// A stale answer (the range was freed and came back as the other kind) is harmless: pinned memory can be staged
+// like pageable memory, and cudaMemcpyAsync accepts pageable memory (the driver then stages it itself).
 bool is_pageable(const void* p)
 {
+    struct Entry { const void* p; bool pageable; };
+    thread_local Entry cache[4] = {};
+    thread_local unsigned next = 0;
+    for (const Entry& e : cache)
+        if (e.p == p && p) return e.pageable;
     cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return true;
-    }
-    return a.type == cudaMemoryTypeUnregistered;
+    bool pageable = true;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) cudaGetLastError();
+    else pageable = a.type == cudaMemoryTypeUnregistered;
+    cache[next++ & 3u] = Entry{p, pageable};
+    return pageable;
 }
+
+constexpr size_t kStagePieceBytes = 384u << 10;   // smallest piece of a strip staged and sent on its own
 
 // One host image of a host-pointer call, validated and cut into strips.
 struct HostJob {
@@ -180,10 +101,11 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         if ((J.stageOut || J.stageOut2) && out > needStageOut) needStageOut = out;
     }
     if (needIn == 0) return GOOFY_B200_OK;
-    int rc = t_pipe.prepare(dev, needIn, needOut);
+    ThreadResources& R = thread_resources(dev);
+    int rc = R.pipe.prepare(dev, needIn, needOut);
     if (rc != GOOFY_B200_OK) return rc;
     if (needStageIn || needStageOut) {
-        rc = t_stage.ensure(needStageIn, needStageOut);
+        rc = R.stage.ensure(needStageIn, needStageOut);
         if (rc != GOOFY_B200_OK) return rc;
     }
 
@@ -191,20 +113,20 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
     auto retire = [&](int slot) -> int {  // wait for the slot's strip and hand its blocks to the caller
         const HostJob* J = pending[slot].job;
         if (!J) return GOOFY_B200_OK;
-        GB_CUDA(cudaStreamSynchronize(t_pipe.stream[slot]));
+        GB_CUDA(cudaStreamSynchronize(R.pipe.stream[slot]));
         if (J->stageOut)
-            CopyPool::get().copy1d(J->result + (size_t)pending[slot].r0 * J->outRowBytes, (const uint8_t*)t_stage.out[slot],
+            CopyPool::get().copy1d(J->result + (size_t)pending[slot].r0 * J->outRowBytes, (const uint8_t*)R.stage.out[slot],
                                    (size_t)pending[slot].rows * J->outRowBytes);
         if (J->stageOut2)
             CopyPool::get().copy1d(J->result2 + (size_t)pending[slot].r0 * J->outRowBytes,
-                                   (const uint8_t*)t_stage.out[slot] + (size_t)J->stripRows * J->outRowBytes,
+                                   (const uint8_t*)R.stage.out[slot] + (size_t)J->stripRows * J->outRowBytes,
                                    (size_t)pending[slot].rows * J->outRowBytes);
         pending[slot].job = nullptr;
         return GOOFY_B200_OK;
     };
     // One strip: stage (if pageable) -> H2D -> kernel -> D2H, all on the slot's stream.
     auto issue = [&](int slot, const HostJob& J, uint32_t r0, uint32_t rows) -> int {
-        cudaStream_t s = t_pipe.stream[slot];
+        cudaStream_t s = R.pipe.stream[slot];
         const uint8_t* src = J.input + (size_t)r0 * 4u * J.stride;
         // the staging strips of this slot are about to be reused (pinned results: stream order protects the device scratch)
         if (pending[slot].job && (J.stageIn || J.stageOut || J.stageOut2 || pending[slot].job->stageOut || pending[slot].job->stageOut2)) {
@@ -212,20 +134,29 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
             if (r != GOOFY_B200_OK) return r;
         }
         if (J.stageIn) {
-            CopyPool::get().copy2d((uint8_t*)t_stage.in[slot], J.rowBytes, src, J.stride, J.rowBytes, (size_t)rows * 4u);
-            GB_CUDA(cudaMemcpyAsync(t_pipe.dIn[slot], t_stage.in[slot], (size_t)rows * 4u * J.rowBytes, cudaMemcpyHostToDevice, s));
+            // staged in up to four pieces, each sent as soon as it is in pinned memory: the DMA of one piece runs under
+            // the staging copy of the next, which is most of what a call on a test-image-sized texture spends
+            const size_t pixelRows = (size_t)rows * 4u;
+            size_t pieces = pixelRows * J.rowBytes / kStagePieceBytes;
+            pieces = pieces < 1u ? 1u : (pieces > 4u ? 4u : pieces);
+            for (size_t k = 0; k < pieces; ++k) {
+                const size_t y0 = pixelRows * k / pieces, y1 = pixelRows * (k + 1u) / pieces;
+                uint8_t* stage = (uint8_t*)R.stage.in[slot] + y0 * J.rowBytes;
+                CopyPool::get().copy2d(stage, J.rowBytes, src + y0 * J.stride, J.stride, J.rowBytes, y1 - y0);
+                GB_CUDA(cudaMemcpyAsync((uint8_t*)R.pipe.dIn[slot] + y0 * J.rowBytes, stage, (y1 - y0) * J.rowBytes, cudaMemcpyHostToDevice, s));
+            }
         } else {
-            GB_CUDA(cudaMemcpy2DAsync(t_pipe.dIn[slot], J.rowBytes, src, J.stride, J.rowBytes, (size_t)rows * 4u, cudaMemcpyHostToDevice, s));
+            GB_CUDA(cudaMemcpy2DAsync(R.pipe.dIn[slot], J.rowBytes, src, J.stride, J.rowBytes, (size_t)rows * 4u, cudaMemcpyHostToDevice, s));
         }
         const size_t half = (size_t)J.stripRows * J.outRowBytes;   // where a dual-output job keeps its ETC1s blocks
-        uint8_t* dOut = (uint8_t*)t_pipe.dOut[slot];
-        const int r = J.result2 ? encode_uniform(gb::kDual, dOut, dOut + half, t_pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s)
-                                : encode_any(codec, dOut, t_pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s);
+        uint8_t* dOut = (uint8_t*)R.pipe.dOut[slot];
+        const int r = J.result2 ? encode_uniform(gb::kDual, dOut, dOut + half, R.pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s)
+                                : encode_any(codec, dOut, R.pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s);
         if (r != GOOFY_B200_OK) return r;
-        GB_CUDA(cudaMemcpyAsync(J.stageOut ? t_stage.out[slot] : (void*)(J.result + (size_t)r0 * J.outRowBytes), dOut,
+        GB_CUDA(cudaMemcpyAsync(J.stageOut ? R.stage.out[slot] : (void*)(J.result + (size_t)r0 * J.outRowBytes), dOut,
                                 (size_t)rows * J.outRowBytes, cudaMemcpyDeviceToHost, s));
         if (J.result2)
-            GB_CUDA(cudaMemcpyAsync(J.stageOut2 ? (void*)((uint8_t*)t_stage.out[slot] + half) : (void*)(J.result2 + (size_t)r0 * J.outRowBytes),
+            GB_CUDA(cudaMemcpyAsync(J.stageOut2 ? (void*)((uint8_t*)R.stage.out[slot] + half) : (void*)(J.result2 + (size_t)r0 * J.outRowBytes),
                                     dOut + half, (size_t)rows * J.outRowBytes, cudaMemcpyDeviceToHost, s));
         pending[slot].job = &J;
         pending[slot].r0 = r0;
@@ -234,7 +165,7 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
     };
     // On failure nothing may still be reading an input or writing a result when the caller gets control back.
     auto fail = [&](int code) -> int {
-        for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(t_pipe.stream[i]);
+        for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(R.pipe.stream[i]);
         cudaGetLastError();
         return code;
     };
@@ -286,18 +217,25 @@ int encode_dual_host(void* resultDxt1, void* resultEtc1, const void* input, uint
 // n host images through ONE pipeline: every image is validated before anything is started.
 int encode_host_batch(int codec, const GoofyB200Image* images, uint32_t n)
 {
-    if (!is_codec(codec)) return GOOFY_B200_E_CODEC;
+    const bool both = codec == GOOFY_B200_BOTH;
+    if (!both && !is_codec(codec)) return GOOFY_B200_E_CODEC;
     if (n == 0u) return GOOFY_B200_OK;
     if (!images) return GOOFY_B200_E_NULL;
     std::vector<HostJob> jobs(n);
     for (uint32_t i = 0; i < n; ++i) {
-        const int rc = make_host_job(codec, images[i].dst, images[i].src, images[i].width, images[i].height, images[i].stride, jobs[i]);
+        const int rc = make_host_job(both ? GOOFY_B200_DXT1 : codec, images[i].dst, images[i].src, images[i].width, images[i].height,
+                                     images[i].stride, jobs[i]);
         if (rc != GOOFY_B200_OK) return rc;
+        if (both && jobs[i].blockRows != 0u) {
+            if (!images[i].dst2) return GOOFY_B200_E_NULL;
+            jobs[i].result2 = (uint8_t*)images[i].dst2;
+            jobs[i].stageOut2 = is_pageable(images[i].dst2);
+        }
     }
     int dev = -1;
     const int rc = ensure_device_ready(&dev);
     if (rc != GOOFY_B200_OK) return rc;
-    return run_host_jobs(codec, jobs.data(), n, dev);
+    return run_host_jobs(both ? GOOFY_B200_DXT1 : codec, jobs.data(), n, dev);
 }
 
 }  // namespace

@@ -33,11 +33,16 @@
 extern "C" {
 #endif
 
-#define GOOFY_B200_ABI_VERSION 1
+#define GOOFY_B200_ABI_VERSION 2   /* 2: GoofyB200Image gained dst2, GOOFY_B200_BOTH */
 
 /* codec selectors */
 #define GOOFY_B200_DXT1 0
 #define GOOFY_B200_ETC1 1
+/* Both codecs from ONE read of every pixel (5 B/px of HBM traffic instead of 9): DXT1 blocks to `dst`, ETC1s blocks
+ * to `dst2`.  Accepted by the batch entry points whose descriptors carry two result pointers
+ * (goofy_b200_encode_batch_device, _batch_sharded, _host_batch); the uniform entry points have
+ * goofy_b200_encode_dual_device / _dual_host / _dual_sharded_host for it. */
+#define GOOFY_B200_BOTH 2
 /* Second flavour: bit-exact with the reference's float "idea" encoder goofyRef::compressDXT1/ETC1
  * (Src/goofy_tc_reference.cpp:794-850) instead of with the SSE2 path.  The two flavours differ
  * by design (rounding, tie-break, minimum range, table thresholds).  Accepted by the host,
@@ -61,11 +66,12 @@ extern "C" {
  * (device < 0: the calling thread's current device). */
 typedef struct GoofyB200Image {
     const void* src; /* RGBA8, 16-byte aligned */
-    void* dst;       /* width*height/2 bytes, 8-byte aligned */
+    void* dst;       /* width*height/2 bytes, 8-byte aligned (GOOFY_B200_BOTH: the DXT1 blocks) */
     uint32_t width;
     uint32_t height;
     uint32_t stride; /* bytes */
     int32_t device;
+    void* dst2;      /* GOOFY_B200_BOTH only: the ETC1s blocks, width*height/2 bytes, 8-byte aligned; ignored otherwise */
 } GoofyB200Image;
 
 int goofy_b200_abi_version(void);
@@ -74,6 +80,11 @@ int goofy_b200_device_count(void);
 const char* goofy_b200_error_string(int code);
 /* Kernels launched by this library in the calling process so far (all threads, all devices). */
 uint64_t goofy_b200_kernel_launches(void);
+/* Sets of host-path scratch (streams, device strips, pinned staging strips, descriptor arena) created in this process
+ * so far.  A host thread leases one set while it lives and returns it to a pool when it exits, so this number tracks
+ * the largest number of threads that were inside the host-pointer / batch entry points at the same time, not the
+ * number of threads that ever called. */
+uint64_t goofy_b200_host_scratch_sets(void);
 
 /* Image load layer used by the uniform device entry points (process-wide):
  *   AUTO    the library picks per shape (default)
@@ -109,7 +120,7 @@ int goofy_b200_encode_host(int codec, void* result, const void* input, uint32_t 
 int goofy_b200_encode_dual_host(void* result_dxt1, void* result_etc1, const void* input, uint32_t width, uint32_t height,
                                 uint32_t stride);
 
-/* n host images (src / dst are HOST pointers here, `device` is ignored) through one pipeline on the calling thread's
+/* n host images (src / dst / dst2 are HOST pointers here, `device` is ignored; codec may be GOOFY_B200_BOTH) through one pipeline on the calling thread's
  * current device: the copies and kernels of neighbouring images overlap, which a loop of single-image calls (each of
  * which waits for its own result) cannot do -- the host-side batch for the reference harness's per-image loop
  * (Src/main.cpp:646-743).  Every image is validated before anything starts; returns when all results are in place. */
@@ -139,7 +150,8 @@ int goofy_b200_encode_dual_device(void* d_result_dxt1, void* d_result_etc1, cons
 
 /* n images of arbitrary shapes on the current device (descs is a HOST array; descs[i].device
  * must be < 0 or the current device).  One launch per call; the descriptor table is copied
- * to the device on `stream`. */
+ * to the device on `stream`.  codec: GOOFY_B200_DXT1, _ETC1, _BOTH (descs[i].dst2 holds the ETC1s blocks) or one
+ * of the float-reference flavours (widths then only need to be multiples of 4). */
 int goofy_b200_encode_batch_device(int codec, const GoofyB200Image* descs, uint32_t n_images, void* stream);
 
 /* ---- the step after the encoder (reference: Src/main.cpp:561-613 decode, :403-469 MSE/PSNR) ---- */
@@ -162,6 +174,9 @@ int goofy_b200_encode_batch_sharded(int codec, const GoofyB200Image* descs, uint
  * encoded on device g through the host path.  n_gpus <= 0 means all visible devices. */
 int goofy_b200_encode_sharded_host(int codec, void* result, const void* input, uint32_t width, uint32_t height,
                                    uint32_t stride, int n_gpus);
+/* Same partition, both codecs from one upload of every strip (goofy_b200_encode_dual_host per device). */
+int goofy_b200_encode_dual_sharded_host(void* result_dxt1, void* result_etc1, const void* input, uint32_t width,
+                                        uint32_t height, uint32_t stride, int n_gpus);
 /* Strip partition used by the scheduler: block rows [first, first+count) for shard `shard`. */
 void goofy_b200_strip_partition(uint32_t height, int n_shards, int shard, uint32_t* first_block_row,
                                 uint32_t* block_row_count);

@@ -43,7 +43,7 @@ inline int compressETC1(unsigned char* result, const unsigned char* input, unsig
 
 namespace b200 {
 
-enum Codec : int { DXT1 = GOOFY_B200_DXT1, ETC1 = GOOFY_B200_ETC1 };
+enum Codec : int { DXT1 = GOOFY_B200_DXT1, ETC1 = GOOFY_B200_ETC1, BOTH = GOOFY_B200_BOTH /* batch entry points: Image::dst2 */ };
 using Image = ::GoofyB200Image;
 
 inline int deviceCount() { return goofy_b200_device_count(); }
@@ -97,6 +97,13 @@ inline int encodeSharded(Codec codec, unsigned char* result, const unsigned char
                          uint32_t stride, int nGpus = 0)
 {
     return goofy_b200_encode_sharded_host(codec, result, input, width, height, stride, nGpus);
+}
+
+// The same partition, both codecs from one upload of every strip.
+inline int encodeDualSharded(unsigned char* resultDxt1, unsigned char* resultEtc1, const unsigned char* input, uint32_t width,
+                             uint32_t height, uint32_t stride, int nGpus = 0)
+{
+    return goofy_b200_encode_dual_sharded_host(resultDxt1, resultEtc1, input, width, height, stride, nGpus);
 }
 
 // DXT1 and ETC1s of one HOST image from a single upload.
