@@ -44,6 +44,8 @@ def parse_args():
                     help="image load layer of the device entry points (see include/goofy_b200.h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the named multi-GPU shapes (configs[3], configs[4], shard scheduler)")
+    ap.add_argument("--images", type=int, default=4096, help="textures of configs[3] (4096 x 1024^2 in BASELINE.json)")
     return ap.parse_args()
 
 
@@ -68,92 +70,116 @@ def hbm_peak():
 
 
 # ----------------------------------------------------------------------------- clocks
+_SAMPLER_CHILD = r"""
+import json, sys, time
+import pynvml as n
+n.nvmlInit()
+h = n.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+sm_max = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+print(json.dumps({"ready": True, "sm_max": sm_max}), flush=True)
+import select
+samples = []
+i = 0
+pw, rs = 0.0, 0
+while True:
+    if i % 8 == 0:
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+            try: rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception: rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        except Exception: pass
+    try: samples.append((time.monotonic(), float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), pw, rs))
+    except Exception: pass
+    i += 1
+    if select.select([sys.stdin], [], [], 0)[0]:
+        break
+    if len(samples) > 2000000: break
+print(json.dumps({"samples": samples}), flush=True)
+"""
+
+
 class ClockSampler:
-    """Samples SM clock, power and throttle reasons of one GPU while the timed region runs.
-    NVML (nvidia_ml_py) every 2 ms in a thread -- the timed region of this bench lasts tens of
-    milliseconds, too short for `nvidia-smi -lms 200`; nvidia-smi is the fallback."""
+    """Samples SM clock, power and throttle reasons of one GPU while the timed regions run.
+
+    The sampling loop lives in a CHILD PROCESS (NVML through nvidia_ml_py, back to back, a few samples per
+    millisecond): a thread of this process only gets the interpreter lock every few milliseconds while the main thread
+    is busy launching, which left 2 samples in a 3.4 ms region.  Samples carry CLOCK_MONOTONIC timestamps (system-wide),
+    so the parent keeps the ones that fall between its own begin / end marks.  Fallback: nvidia-smi, then nothing."""
 
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.samples = []
-        self.stop_flag = threading.Event()
-        self.thread = None
-        self.nvml = None
-        self.handle = None
+        self.proc = None
         self.sm_max = None
-        self._last = None
-
-    def start(self):
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            idx = self.gpu
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            if vis:
-                try:
-                    idx = int(vis.split(",")[self.gpu])
-                except (ValueError, IndexError):
-                    idx = self.gpu
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
-            self.nvml = pynvml
-        except Exception:
-            self.nvml = None
-        self.thread = threading.Thread(target=self._run_nvml if self.nvml else self._run_smi, daemon=True)
-        self.thread.start()
-
-    def _sample_nvml(self, with_power=True):
-        n = self.nvml
-        try:
-            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-            if with_power or self._last is None:
-                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
-                try:
-                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                except Exception:
-                    rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                self._last = (pw, rs)
-            self.samples.append((sm, self._last[0], self._last[1]))
-        except Exception:
-            pass
-
-    def _run_nvml(self):
-        # SM clock every 2 ms; power and throttle reasons (slower queries on some drivers) every 8th sample
-        i = 0
-        while not self.stop_flag.is_set():
-            self._sample_nvml(with_power=(i % 8 == 0))
-            i += 1
-            time.sleep(0.002)
-
-    def _run_smi(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
-        while not self.stop_flag.is_set():
+        self.marks = {}
+        idx = gpu_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.sm_max = float(out[1])
-                self.samples.append((float(out[0]), float(out[2]), int(out[3].strip(), 16)))
-            except Exception:
-                return
+                idx = int(vis.split(",")[gpu_index])
+            except (ValueError, IndexError):
+                idx = gpu_index
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_CHILD, str(idx)], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            ready = json.loads(self.proc.stdout.readline())
+            self.sm_max = ready["sm_max"]
+        except Exception:
+            self.proc = None
 
-    def stop(self) -> dict:
-        self.stop_flag.set()
-        if self.thread is not None:
-            self.thread.join(timeout=6)
-        if self.nvml and len(self.samples) < 2:
-            self._sample_nvml()   # very short timed regions: make sure there is at least one reading
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
-        sm = [x[0] for x in self.samples]
+    def begin(self, name: str):
+        self.marks[name] = [time.monotonic(), None]
+
+    def end(self, name: str):
+        self.marks[name][1] = time.monotonic()
+
+    # timed() brackets its region with these two
+    def start(self):
+        self.begin("headline")
+
+    def stop_region(self):
+        self.end("headline")
+
+    def finish(self, span_name: str = "headline") -> dict:
+        """Stop the child and summarise the samples inside the `span_name` marks (and count the headline's)."""
+        samples = []
+        if self.proc is not None:
+            try:
+                self.proc.stdin.write("stop\n")
+                self.proc.stdin.flush()
+                samples = json.loads(self.proc.stdout.readline())["samples"]
+                self.proc.wait(timeout=5)
+            except Exception:
+                samples = []
+        if not samples:
+            return self._smi_once()
+        t0, t1 = self.marks.get(span_name, self.marks.get("headline"))
+        h0, h1 = self.marks["headline"]
+        inside = [x for x in samples if t0 <= x[0] <= (t1 or x[0])]
+        head = [x for x in samples if h0 <= x[0] <= (h1 or x[0])]
+        use = inside or samples[-3:]
+        sm = [x[1] for x in use]
         bits = 0
-        for x in self.samples:
-            bits |= x[2]
+        for x in use:
+            bits |= int(x[3])
         return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": self.sm_max,
-                "power_w_max": float(max(x[1] for x in self.samples)), "samples": len(sm),
-                "source": "nvml" if self.nvml else "nvidia-smi",
+                "power_w_max": float(max(x[2] for x in use)), "samples": len(inside), "samples_in_headline_region": len(head),
+                "headline_sm_mhz": float(np.median([x[1] for x in head])) if head else None,
+                "source": "nvml (child process, CLOCK_MONOTONIC-stamped)",
                 "reasons": [name for name, bit in self.REASONS if bits & bit]}
+
+    def _smi_once(self) -> dict:
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                 capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+            bits = int(out[3].strip(), 16)
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "power_w_max": float(out[2]), "samples": 1,
+                    "source": "nvidia-smi (one reading after the timed regions: NVML sampler unavailable)",
+                    "reasons": [name for name, bit in self.REASONS if bits & bit]}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
 
 
 def bind_to_gpu_numa_node(local_rank: int):
@@ -274,21 +300,344 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- B200 arm
+class Ctx:
+    """Everything the legs of the B200 arm share: device, rank, timing helpers."""
+
+    def __init__(self, args):
+        import torch
+
+        import goofy_b200 as gb
+        self.torch, self.gb, self.args = torch, gb, args
+        self.rank, self.local_rank, self.world = dist_env()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.distributed = self.world > 1
+        self.numa = bind_to_gpu_numa_node(self.local_rank) if self.distributed else None
+        self.dist = None
+        self.host_group = None
+        if self.distributed:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+            # a second, CPU-side group: ranks that merely wait for rank 0 must not do it inside an NCCL kernel that
+            # spins on their GPU (rank 0 may be using that GPU through the in-library shard scheduler)
+            self.host_group = dist.new_group(backend="gloo")
+        from goofy_b200 import _lib
+        self.lib = _lib.load()          # raw ctypes entry points: pointers and the stream as plain integers, so a
+        self.stream = int(torch.cuda.current_stream().cuda_stream)   # 20 us launch is not waiting for Python
+
+    def barrier(self):
+        if self.distributed:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        """Wait for the other ranks on the CPU (gloo), GPUs idle."""
+        self.torch.cuda.synchronize()
+        if self.distributed:
+            self.dist.barrier(group=self.host_group)
+
+    def all_max(self, x: float) -> float:
+        if not self.distributed:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, ok: bool) -> bool:
+        if not self.distributed:
+            return bool(ok)
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def timed(self, fn, steps, warmup, sampler=None, collective=True):
+        """W warm-up steps, then K steps between two CUDA events on the launching stream, barrier + synchronize on
+        both sides, MAX over ranks.  collective=False: this rank alone (the others are parked at a barrier)."""
+        torch, gb = self.torch, self.gb
+        for _ in range(warmup):
+            fn()
+        self.barrier() if collective else torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.start()      # clocks are sampled during the timed region only
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = gb.kernel_launches()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier() if collective else torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.stop_region()
+        ms = e0.elapsed_time(e1)
+        launches = gb.kernel_launches() - l0
+        return (self.all_max(ms) if collective else ms), launches
+
+
+def reference_blocks(codec: int, img: np.ndarray, w: int, h: int, stride: int) -> np.ndarray:
+    """The checker of the bit-exactness samples: the unmodified reference (oracle/_ref) where it was built, else the
+    scalar oracle.  Test infrastructure -- never on a timed path."""
+    from oracle.oracle import Oracle, Reference, aligned_copy
+    if Reference.available():
+        ref = Reference()
+        rc, out = ref.compress_mt(codec, aligned_copy(img), w, h, stride, max(1, min(8, ref.hardware_threads() or 1)))
+    else:
+        rc, out = Oracle().compress(codec, aligned_copy(img), w, h, stride)
+    assert rc == 0
+    return out
+
+
+def config_batch1024(ctx: Ctx, steps: int, warmup: int, n_images: int):
+    """BASELINE.json configs[3]: `n_images` textures of 1024 x 1024, DXT1 + ETC1s, partitioned by texture over the ranks
+    (goofy_b200.sharding.batch_partition; GoofyTC/goofy_tc.h:1514-1524 has no cross-block state to exchange).
+    Strong scaling: the total is fixed.  Timed: the dual-output kernel (one read of every pixel, 5 B/px) and the two
+    single-codec passes (9 B/px); checked: a sample of this rank's shard against the reference, both codecs."""
+    torch, gb = ctx.torch, ctx.gb
+    from goofy_b200 import sharding
+    w = h = 1024
+    img_bytes, out_bytes = w * h * 4, w * h // 2
+
+    def make_shard(indices):
+        n = len(indices)
+        src = torch.empty((n, h, w, 4), dtype=torch.uint8, device=ctx.dev)
+        distinct = min(n, 16)
+        for i in range(distinct):
+            fill_texture_device(torch, src[i], seed=7 * (indices.start + i) + 1)
+        if n > distinct:   # a few textures of the stress families S0 (uniform random) and S2 (0 / 255), SURVEY.md 8(d)
+            g = torch.Generator(device=ctx.dev)
+            g.manual_seed(1234 + indices.start)
+            src[distinct - 2] = torch.randint(0, 256, (h, w, 4), device=ctx.dev, dtype=torch.int32, generator=g).to(torch.uint8)
+            src[distinct - 1] = (torch.randint(0, 2, (h, w, 4), device=ctx.dev, dtype=torch.int32, generator=g) * 255).to(torch.uint8)
+        for i in range(distinct, n):
+            src[i].copy_(src[i % distinct])
+        return src, torch.empty((n, out_bytes), dtype=torch.uint8, device=ctx.dev), torch.empty((n, out_bytes), dtype=torch.uint8, device=ctx.dev)
+
+    def runners(src, d1, d2):
+        n = src.shape[0]
+        ps, p1, p2 = int(src.data_ptr()), int(d1.data_ptr()), int(d2.data_ptr())
+        lib, st = ctx.lib, ctx.stream
+
+        def dual():
+            gb.check(lib.goofy_b200_encode_dual_device(p1, p2, ps, w, h, w * 4, img_bytes, out_bytes, n, st))
+
+        def two_passes():
+            gb.check(lib.goofy_b200_encode_batch_uniform_device(gb.DXT1, p1, ps, w, h, w * 4, img_bytes, out_bytes, n, st))
+            gb.check(lib.goofy_b200_encode_batch_uniform_device(gb.ETC1, p2, ps, w, h, w * 4, img_bytes, out_bytes, n, st))
+        return dual, two_passes
+
+    mine = sharding.batch_partition(n_images, ctx.world, ctx.rank)
+    src, d1, d2 = make_shard(mine)
+    dual, two_passes = runners(src, d1, d2)
+    total_px = n_images * w * h
+    ms_d, launches = ctx.timed(dual, steps, warmup)
+    kernel = gb.last_launch_kernel()
+    ms_t, _ = ctx.timed(two_passes, steps, warmup)
+    # bit-exactness of a sample of this rank's shard: first, a stress-family and the last texture, both codecs
+    dual()
+    torch.cuda.synchronize()
+    ok = True
+    n = len(mine)
+    for i in sorted({0, min(n - 1, 14), min(n - 1, 15), n - 1}):
+        host = src[i].cpu().numpy()
+        ok = ok and np.array_equal(d1[i].cpu().numpy(), reference_blocks(0, host, w, h, w * 4))
+        ok = ok and np.array_equal(d2[i].cpu().numpy(), reference_blocks(1, host, w, h, w * 4))
+    two_passes()
+    a1, a2 = d1.clone(), d2.clone()
+    dual()
+    torch.cuda.synchronize()
+    ok = ok and bool(torch.equal(a1, d1) and torch.equal(a2, d2))
+    ok = ctx.all_true(ok)
+    del a1, a2
+    out = {
+        "workload": f"{n_images} x 1024x1024 RGBA8, DXT1+ETC1s, textures partitioned over {ctx.world} GPU(s) (BASELINE.json configs[3])",
+        "scaling": "strong", "sharding": "batch_partition (contiguous texture ranges, no collectives)",
+        "value": total_px * steps / (ms_d * 1e-3) / 1e6, "unit": "MP/s (each pixel to DXT1 AND ETC1s)", "ms_per_step": ms_d / steps,
+        "kernel": kernel, "bytes_per_pixel": 5.0, "achieved_gbs_per_gpu": total_px / ctx.world * 5.0 * steps / (ms_d * 1e-3) / 1e9,
+        "two_passes": {"value": total_px * steps / (ms_t * 1e-3) / 1e6, "bytes_per_pixel": 9.0,
+                       "achieved_gbs_per_gpu": total_px / ctx.world * 9.0 * steps / (ms_t * 1e-3) / 1e9},
+        "bit_exact": ok, "bit_exact_sample": "4 textures of every rank's shard vs the reference (both codecs), and dual == two passes on the whole shard",
+        "steps": steps, "gpu_launches": int(launches),
+    }
+    if ctx.world > 1:
+        # the same workload on ONE GPU of this box (rank 0, the others parked at the barrier): the denominator of the efficiency
+        del src, d1, d2
+        torch.cuda.empty_cache()
+        v1 = None
+        if ctx.rank == 0:
+            src, d1, d2 = make_shard(range(n_images))
+            dual1, _ = runners(src, d1, d2)
+            ms1, _ = ctx.timed(dual1, max(3, steps // 2), 2, collective=False)
+            v1 = total_px * max(3, steps // 2) / (ms1 * 1e-3) / 1e6
+            del src, d1, d2
+            torch.cuda.empty_cache()
+        ctx.host_barrier()
+        if ctx.rank == 0:
+            out["n1_value_same_box"] = v1
+            out["efficiency_vs_n1_per_gpu"] = out["value"] / (ctx.world * v1)
+    return out
+
+
+def config_strip16384(ctx: Ctx, steps: int, warmup: int):
+    """BASELINE.json configs[4]: one 16384 x 16384 texture whose rows are 65 792 bytes apart (pad bytes 0xAB), DXT1,
+    strip g of N on rank g (goofy_b200_strip_partition).  Strong scaling.  Checked: the first and the last 64 rows of
+    this rank's strip against the reference run on the same padded rows."""
+    torch, gb = ctx.torch, ctx.gb
+    w = h = 16384
+    stride = w * 4 + 256
+
+    def make_strip(first, count, seed):
+        rows = count * 4
+        buf = torch.full((rows, stride), 0xAB, dtype=torch.uint8, device=ctx.dev)
+        for y0 in range(0, rows, 2048):
+            y1 = min(rows, y0 + 2048)
+            tex = torch.empty((y1 - y0, w, 4), dtype=torch.uint8, device=ctx.dev)
+            fill_texture_device(torch, tex, seed=seed + first * 4 + y0)
+            buf[y0:y1, : w * 4] = tex.view(y1 - y0, w * 4)
+            del tex
+        return buf, torch.empty(rows * w // 2, dtype=torch.uint8, device=ctx.dev)
+
+    def runner(buf, dst):
+        pb, pd, rows = int(buf.data_ptr()), int(dst.data_ptr()), buf.shape[0]
+        lib, st = ctx.lib, ctx.stream
+        return lambda: gb.check(lib.goofy_b200_encode_device(gb.DXT1, pd, pb, w, rows, stride, st))
+
+    first, count = gb.strip_partition(h, ctx.world, ctx.rank)
+    buf, dst = make_strip(first, count, 31)
+    strip = runner(buf, dst)
+    ms, launches = ctx.timed(strip, steps, warmup)
+    kernel = gb.last_launch_kernel()
+    strip()
+    torch.cuda.synchronize()
+    ok = True
+    rows = count * 4
+    for y0 in sorted({0, rows - 64}):
+        host = buf[y0:y0 + 64].cpu().numpy()
+        want = reference_blocks(0, host, w, 64, stride)
+        got = dst[(y0 // 4) * (w // 4) * 8: (y0 // 4 + 16) * (w // 4) * 8].cpu().numpy()
+        ok = ok and np.array_equal(got, want)
+    ok = ctx.all_true(ok)
+    total_px = w * h
+    out = {
+        "workload": f"16384x16384 RGBA8, stride {stride} B (pad 0xAB), DXT1, {ctx.world} strip(s) of whole block rows (BASELINE.json configs[4])",
+        "scaling": "strong", "sharding": "strip_partition (rows [2048g, 2048(g+1)) at 8 GPUs, no collectives)",
+        "value": total_px * steps / (ms * 1e-3) / 1e6, "unit": "MP/s", "ms_per_step": ms / steps, "kernel": kernel,
+        "bytes_per_pixel": BYTES_PER_PIXEL, "achieved_gbs_per_gpu": total_px / ctx.world * BYTES_PER_PIXEL * steps / (ms * 1e-3) / 1e9,
+        "strip_rows_per_gpu": rows, "stride": stride,
+        "bit_exact": ok, "bit_exact_sample": "first and last 64 pixel rows of every rank's strip vs the reference on the same padded rows",
+        "steps": steps, "gpu_launches": int(launches),
+    }
+    if ctx.world > 1:
+        del buf, dst
+        torch.cuda.empty_cache()
+        v1 = None
+        if ctx.rank == 0:
+            buf, dst = make_strip(0, h // 4, 31)
+            whole = runner(buf, dst)
+            k = max(3, steps // 2)
+            ms1, _ = ctx.timed(whole, k, 2, collective=False)
+            v1 = total_px * k / (ms1 * 1e-3) / 1e6
+            del buf, dst
+            torch.cuda.empty_cache()
+        ctx.host_barrier()
+        if ctx.rank == 0:
+            out["n1_value_same_box"] = v1
+            out["efficiency_vs_n1_per_gpu"] = out["value"] / (ctx.world * v1)
+    return out
+
+
+def sharded_api_leg(ctx: Ctx):
+    """The in-library scheduler (one host thread per device, DeviceWorker in host_batch.cuh) across ALL devices this
+    process can see, called by rank 0 alone while the other ranks wait: goofy_b200_encode_batch_sharded on textures
+    resident on every device (both codecs from one read) and goofy_b200_encode_sharded_host on one host image in strips.
+    Both checked against the reference."""
+    torch, gb = ctx.torch, ctx.gb
+    out = None
+    ctx.host_barrier()     # every rank's GPU is idle from here until the closing host barrier
+    if ctx.rank == 0:
+        n_dev = gb.device_count()
+        w = h = 1024
+        per_dev = 8
+        keep, descs = [], []
+        for d in range(n_dev):
+            with torch.cuda.device(d):
+                for k in range(per_dev):
+                    s = torch.empty((h, w, 4), dtype=torch.uint8, device=f"cuda:{d}")
+                    fill_texture_device(torch, s, seed=900 + per_dev * d + k)
+                    a = torch.zeros(w * h // 2, dtype=torch.uint8, device=f"cuda:{d}")
+                    b = torch.zeros(w * h // 2, dtype=torch.uint8, device=f"cuda:{d}")
+                    keep.append((s, a, b))
+                    descs.append((s, a, w, h, w * 4, d, b))
+                torch.cuda.synchronize(d)
+        arr = gb.make_descriptors(descs)
+        gb.check(gb.encode_batch_sharded(gb.BOTH, arr))
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            gb.check(gb.encode_batch_sharded(gb.BOTH, arr))
+        dt = (time.perf_counter() - t0) / reps
+        ok = True
+        for i in sorted({0, len(keep) // 2, len(keep) - 1}):
+            s, a, b = keep[i]
+            host = s.cpu().numpy()
+            ok = ok and np.array_equal(a.cpu().numpy(), reference_blocks(0, host, w, h, w * 4))
+            ok = ok and np.array_equal(b.cpu().numpy(), reference_blocks(1, host, w, h, w * 4))
+        # one host image (pinned), strips of whole block rows, strip g on device g
+        hw, hh = 8192, 2048
+        h_src = torch.empty((hh, hw, 4), dtype=torch.uint8).pin_memory()
+        h_dst = torch.empty(hw * hh // 2, dtype=torch.uint8).pin_memory()
+        with torch.cuda.device(0):
+            tmp = torch.empty((hh, hw, 4), dtype=torch.uint8, device="cuda:0")
+            fill_texture_device(torch, tmp, seed=77)
+            h_src.copy_(tmp.cpu())
+            del tmp
+        gb.check(gb.encode_sharded_host(gb.DXT1, h_dst, h_src, hw, hh, hw * 4, n_dev))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            gb.check(gb.encode_sharded_host(gb.DXT1, h_dst, h_src, hw, hh, hw * 4, n_dev))
+        dth = (time.perf_counter() - t0) / reps
+        band = 256
+        for y0 in (0, hh - band):
+            want = reference_blocks(0, h_src[y0:y0 + band].numpy(), hw, band, hw * 4)
+            ok = ok and np.array_equal(h_dst[(y0 // 4) * (hw // 4) * 8: ((y0 + band) // 4) * (hw // 4) * 8].numpy(), want)
+        out = {"n_devices": n_dev, "bit_exact": bool(ok),
+               "batch_sharded": {"call": "goofy_b200_encode_batch_sharded(GOOFY_B200_BOTH)", "textures": len(keep), "texture": [w, h],
+                                 "value": len(keep) * w * h / dt / 1e6, "unit": "MP/s (host wall clock per call, each pixel to both codecs)"},
+               "sharded_host": {"call": "goofy_b200_encode_sharded_host(DXT1)", "image": [hw, hh], "value": hw * hh / dth / 1e6,
+                                "unit": "MP/s (host wall clock per call, pinned host buffers in and out)"}}
+        del keep
+        torch.cuda.set_device(ctx.local_rank)
+    ctx.host_barrier()
+    return out
+
+
+def pcie_probe(ctx: Ctx, size: int):
+    """What the bare copies of one end-to-end step take on this box at this N: 4 B/px pinned host -> device and 0.5 B/px
+    device -> pinned host, issued concurrently on two streams, every rank at the same time, MAX over ranks."""
+    torch = ctx.torch
+    n_in, n_out = size * size * 4, size * size // 2
+    h_in = torch.empty(n_in, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n_out, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n_in, dtype=torch.uint8, device=ctx.dev)
+    d_out = torch.empty(n_out, dtype=torch.uint8, device=ctx.dev)
+    s2 = torch.cuda.Stream(device=ctx.dev)
+
+    def both():
+        d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s2)
+    ms, _ = ctx.timed(both, 5, 2)
+    return ms / 5
+
+
 def run_b200_arm(args):
-    import torch
-
-    import goofy_b200 as gb
-
-    rank, local_rank, world = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    distributed = world > 1
-    numa = bind_to_gpu_numa_node(local_rank) if distributed else None
-    if distributed:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    ctx = Ctx(args)
+    torch, gb = ctx.torch, ctx.gb
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    lib, st = ctx.lib, ctx.stream
+    timed = ctx.timed
 
     gb.set_load_path({"auto": gb.LOAD_AUTO, "direct": gb.LOAD_DIRECT, "tma": gb.LOAD_TMA, "oneshot": gb.LOAD_ONESHOT, "async": gb.LOAD_ASYNC}[args.load_path])
     codec = gb.DXT1 if args.codec == "dxt1" else gb.ETC1
@@ -305,45 +654,25 @@ def run_b200_arm(args):
     torch.cuda.synchronize()
 
     img_bytes = size * size * 4
+    p_src, p_dst = int(src.data_ptr()), int(dst.data_ptr())
 
     def step(c=codec):
         # one pass over the batch through the batched device-resident entry point (one launch)
-        gb.check(gb.encode_batch_uniform_device(c, dst, src, size, size, stride, img_bytes, out_bytes, batch))
+        gb.check(lib.goofy_b200_encode_batch_uniform_device(c, p_dst, p_src, size, size, stride, img_bytes, out_bytes, batch, st))
 
     def step_per_texture(c=codec):
         # the same batch as one call (and one launch) per 8192^2 texture
         for b in range(batch):
-            gb.check(gb.encode_device(c, dst[b], src[b], size, size, stride))
+            gb.check(lib.goofy_b200_encode_device(c, p_dst + b * out_bytes, p_src + b * img_bytes, size, size, stride, st))
 
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup, sampler=None):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        if sampler is not None:
-            sampler.start()      # clocks are sampled during the timed region only
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = gb.kernel_launches()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        launches = gb.kernel_launches() - l0
-        if distributed:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # Clocks: one NVML reading takes milliseconds on this driver and the headline region of a 20-step run lasts 3.4 ms,
+    # so the sampler (a child process) keeps going through every timed leg of this run (device-resident side legs,
+    # end-to-end legs, named configs) and reports how many of its samples fell inside the headline region.
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.begin("all_legs")
     ms, launches = timed(step, args.steps, args.warmup, sampler)
-    clocks = sampler.stop() if rank == 0 else None
+    headline_kernel = gb.last_launch_kernel()
 
     total_px = px_per_step * args.steps * world
     value = total_px / (ms * 1e-3) / 1e6
@@ -352,11 +681,12 @@ def run_b200_arm(args):
     bytes_per_launch = px_per_step * BYTES_PER_PIXEL / launches_per_step
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = hbm_peak()
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu capture
+    traffic, traffic_src = None, None   # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu capture
     try:
         tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
         if size == 8192 and batch == 4:
             traffic = tj["dram_bytes_per_launch"].get(args.codec)
+            traffic_src = "profiles/traffic.json: ncu --set full capture of this launch shape (" + str(tj.get("source", "committed under profiles/")) + "), not re-measured by this run"
     except Exception:
         traffic = None
 
@@ -364,21 +694,24 @@ def run_b200_arm(args):
     side_steps = max(min(args.steps // 2, 100), 3)
     ms_s, launches_s = timed(step_per_texture, side_steps, 3)
     value_s = px_per_step * side_steps * world / (ms_s * 1e-3) / 1e6
+    per_texture_kernel = gb.last_launch_kernel()
 
     # the other codec, same protocol (BASELINE.json's metric names both)
     other = gb.ETC1 if codec == gb.DXT1 else gb.DXT1
-    side_steps = max(min(args.steps // 2, 100), 3)
     ms_o, _ = timed(lambda: step(other), side_steps, 3)
     value_o = px_per_step * side_steps * world / (ms_o * 1e-3) / 1e6
     achieved_o = value_o / world * 1e6 * BYTES_PER_PIXEL / 1e9
+    other_kernel = gb.last_launch_kernel()
 
     # dual-output pass: both codecs from one read (5 B/px)
     dst2 = torch.empty((batch, out_bytes), dtype=torch.uint8, device=dev)
+    p_dst2 = int(dst2.data_ptr())
 
     def dual_step():
-        gb.check(gb.encode_dual_device(dst, dst2, src, size, size, stride, img_bytes, out_bytes, batch))
+        gb.check(lib.goofy_b200_encode_dual_device(p_dst, p_dst2, p_src, size, size, stride, img_bytes, out_bytes, batch, st))
     ms_d, _ = timed(dual_step, side_steps, 3)
     value_d = px_per_step * side_steps * world / (ms_d * 1e-3) / 1e6
+    dual_kernel = gb.last_launch_kernel()
 
     # ---- end to end through the drop-in host API: pinned host buffers, H2D + D2H inside the timed region
     e2e = None
@@ -392,9 +725,13 @@ def run_b200_arm(args):
             gb.check(host_fn(h_dst, h_src, size, size, stride))
         e2e_steps = max(3, min(args.steps, 10))
         ms_e, _ = timed(e2e_step, e2e_steps, 3)
+        pcie_ms = pcie_probe(ctx, size)
         e2e = {"value": size * size * e2e_steps * world / (ms_e * 1e-3) / 1e6, "unit": "MP/s",
                "h2d_bytes_per_step": size * size * 4, "d2h_bytes_per_step": out_bytes,
                "ms_per_step": ms_e / e2e_steps,
+               "pcie_bound_ms": pcie_ms, "ms_per_step_over_pcie_bound": (ms_e / e2e_steps) / pcie_ms,
+               "pcie_bound_note": "bare pinned cudaMemcpyAsync of the same bytes (4 B/px in, 0.5 B/px out, concurrently) on this box, "
+                                  f"all {world} rank(s) at the same time, max over ranks",
                "api": f"goofy_b200.compress{args.codec.upper()}(result, input, w, h, stride) on pinned host buffers"}
         # both codecs from one upload (goofy_b200_encode_dual_host): 4 B/px in, 1 B/px out
         h_dual = torch.empty((2, out_bytes), dtype=torch.uint8).pin_memory()
@@ -406,11 +743,11 @@ def run_b200_arm(args):
                                         "unit": "MP/s (each pixel to DXT1 AND ETC1s, one upload)", "ms_per_step": ms_d2 / e2e_steps,
                                         "d2h_bytes_per_step": 2 * out_bytes}
         # same call with ordinary (pageable) numpy buffers: the library stages them through pinned strips
-        p_src = src[0].cpu().numpy().reshape(-1)
-        p_dst = np.zeros(out_bytes, dtype=np.uint8)
+        p_srcbuf = src[0].cpu().numpy().reshape(-1)
+        p_dstbuf = np.zeros(out_bytes, dtype=np.uint8)
 
         def e2e_pageable_step():
-            gb.check(host_fn(p_dst, p_src, size, size, stride))
+            gb.check(host_fn(p_dstbuf, p_srcbuf, size, size, stride))
         ms_p, _ = timed(e2e_pageable_step, e2e_steps, 2)
         e2e["pageable_buffers"] = {"value": size * size * e2e_steps * world / (ms_p * 1e-3) / 1e6, "unit": "MP/s",
                                    "ms_per_step": ms_p / e2e_steps}
@@ -418,6 +755,25 @@ def run_b200_arm(args):
         gb.check(gb.encode_device(codec, dst[0], src[0], size, size, stride))
         torch.cuda.synchronize()
         e2e["matches_device_path"] = bool(torch.equal(dst[0].cpu(), h_dst))
+        del h_src, h_dst, h_dual
+
+    # ---- the named multi-GPU shapes (outside the headline region): BASELINE.json configs[3] and [4], and the
+    #      in-library shard scheduler; every one with a bit-exactness sample against the reference
+    configs = None
+    sharded = None
+    if not args.no_configs:
+        del src, dst, dst2
+        torch.cuda.empty_cache()
+        cfg_steps = max(3, min(args.steps, 20))
+        configs = {"batch1024": config_batch1024(ctx, cfg_steps, 3, args.images),
+                   "strip16384": config_strip16384(ctx, cfg_steps, 3)}
+        sharded = sharded_api_leg(ctx)
+
+    clocks = None
+    if rank == 0:
+        sampler.end("all_legs")
+        clocks = sampler.finish("all_legs")
+        clocks["span"] = "every timed leg of this run on the GPU (headline, per-texture, other codec, dual-output, end-to-end, named configs)"
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): the unmodified reference
     cpu = None
@@ -434,7 +790,7 @@ def run_b200_arm(args):
                    "single_thread": {"value": one, "cores": 1, "sample": f"same texture, best of 6, as shipped"}}
         else:
             o = Oracle()
-            img = src[0, :1024].cpu().numpy()
+            img = np.zeros((1024, size, 4), dtype=np.uint8)
             t0 = time.perf_counter()
             o.compress(codec, img, size, 1024)
             dtc = time.perf_counter() - t0
@@ -455,11 +811,10 @@ def run_b200_arm(args):
                              f"({int(px_per_step * BYTES_PER_PIXEL) >> 20} MiB per step vs 126 MB of L2)",
                        "load_path": args.load_path,
                        "sharding": "one batch per rank, no collectives" if world > 1 else "single GPU",
-                       "cpu_binding": numa},
+                       "cpu_binding": ctx.numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "kernel": ("encode_direct_kernel" if codec == gb.DXT1 and args.load_path in ("auto", "oneshot")
-                                    else "encode_tma_kernel" if args.load_path == "tma" else "encode_rows_kernel") + f"<{args.codec}>",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "kernel": headline_kernel, "kernel_source": "goofy_b200_last_launch_kernel() after the timed region",
                          "bytes_per_launch": bytes_per_launch, "launch_ms": launch_ms,
                          "like_for_like_ceiling": "tools/membench (profiles/r01_membench.txt): a trivial-compute kernel with the same "
                                                   "8:1 read:write access pattern reaches 7115 GB/s at 1.2 GB per launch "
@@ -467,20 +822,23 @@ def run_b200_arm(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "per_texture_launch": {"value": value_s, "unit": "MP/s", "launches_per_step": launches_s / side_steps,
-                                   "achieved_gbs_per_gpu": value_s / world * 1e6 * BYTES_PER_PIXEL / 1e9,
+                                   "achieved_gbs_per_gpu": value_s / world * 1e6 * BYTES_PER_PIXEL / 1e9, "kernel": per_texture_kernel,
                                    "note": "same batch, one goofy_b200_encode_device call per texture"},
             "other_codec": {"codec": "etc1" if codec == gb.DXT1 else "dxt1", "value": value_o, "unit": "MP/s",
-                            "achieved_gbs_per_gpu": achieved_o, "frac": achieved_o / peak},
+                            "achieved_gbs_per_gpu": achieved_o, "frac": achieved_o / peak, "kernel": other_kernel},
             "dual_output": {"value": value_d, "unit": "MP/s (each pixel encoded to both DXT1 and ETC1s)",
-                            "achieved_gbs_per_gpu": value_d / world * 1e6 * 5.0 / 1e9},
+                            "achieved_gbs_per_gpu": value_d / world * 1e6 * 5.0 / 1e9, "kernel": dual_kernel},
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if configs is not None:
+            line["configs"] = configs
+            line["sharded_api"] = sharded
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    if distributed:
-        dist.destroy_process_group()
+    if ctx.distributed:
+        ctx.dist.destroy_process_group()
     return 0
 
 

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "goofy_b200_error_string": (C.c_char_p, [_int]),
     "goofy_b200_kernel_launches": (_u64, []),
     "goofy_b200_host_scratch_sets": (_u64, []),
+    "goofy_b200_last_launch_kernel": (C.c_char_p, []),
     "goofy_b200_set_load_path": (_int, [_int]),
     "goofy_b200_get_load_path": (_int, []),
     "goofy_b200_compress_dxt1": (_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_uint]),

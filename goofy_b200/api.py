@@ -47,6 +47,11 @@ def kernel_launches() -> int:
     return int(_lib.load().goofy_b200_kernel_launches())
 
 
+def last_launch_kernel() -> str:
+    """The encode kernel this thread launched last through the library (what a call actually ran)."""
+    return _lib.load().goofy_b200_last_launch_kernel().decode()
+
+
 def host_scratch_sets() -> int:
     """Scratch sets of the host paths created so far (they are pooled and leased per thread)."""
     return int(_lib.load().goofy_b200_host_scratch_sets())

@@ -44,6 +44,8 @@ int goofy_b200_device_count(void) { return device_count(); }
 
 uint64_t goofy_b200_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
+const char* goofy_b200_last_launch_kernel(void) { return t_lastKernel; }
+
 uint64_t goofy_b200_host_scratch_sets(void) { return ResourcePool::get().created(); }
 
 int goofy_b200_set_load_path(int path)

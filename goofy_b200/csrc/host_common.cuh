@@ -5,6 +5,9 @@
 namespace {
 
 std::atomic<uint64_t> g_launches{0};
+// what the calling thread launched last (goofy_b200_last_launch_kernel): set by every launcher, so a benchmark can
+// report the kernel a call actually ran instead of guessing it from its flags
+thread_local const char* t_lastKernel = "";
 
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? GOOFY_B200_OK : GOOFY_B200_E_CUDA_BASE - (int)e; }
 

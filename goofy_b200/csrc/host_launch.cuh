@@ -6,8 +6,9 @@
 namespace {
 
 template <typename Kernel>
-int launch_encode(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, const gb::EncodeParams& P)
+int launch_encode(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, const gb::EncodeParams& P, const char* name)
 {
+    t_lastKernel = name;
     static const bool pdl = []() { const char* e = getenv("GOOFY_B200_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -24,26 +25,30 @@ int launch_encode(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, con
     return cuda_rc(e);
 }
 
+template <int MODE>
+constexpr const char* kernel_name(const char* dxt1, const char* etc1, const char* dual) { return MODE == gb::kDxt1 ? dxt1 : MODE == gb::kEtc1 ? etc1 : dual; }
+#define GB_KNAME(base) kernel_name<MODE>(base "<dxt1>", base "<etc1s>", base "<dxt1+etc1s>")
+
 template <int MODE, bool PITCHED>
 int launch_direct_grid(const gb::EncodeParams& Q, dim3 grid, dim3 block, cudaStream_t stream)
 {
     // 32-bit in-image offsets unless the image spans 4 GiB or more
     const bool narrow = (uint64_t)Q.bh * 4u * Q.stride + (uint64_t)Q.bw * 16u < 0xFFFFFFFFull;
     if (Q.firstWave != 0u)   // short launch: the instantiation with the L2 warm-up
-        return narrow ? launch_encode(gb::encode_direct_kernel<MODE, false, PITCHED, true>, grid, block, stream, Q)
-                      : launch_encode(gb::encode_direct_kernel<MODE, true, PITCHED, true>, grid, block, stream, Q);
-    return narrow ? launch_encode(gb::encode_direct_kernel<MODE, false, PITCHED, false>, grid, block, stream, Q)
-                  : launch_encode(gb::encode_direct_kernel<MODE, true, PITCHED, false>, grid, block, stream, Q);
+        return narrow ? launch_encode(gb::encode_direct_kernel<MODE, false, PITCHED, true>, grid, block, stream, Q, GB_KNAME("encode_direct_kernel[short launch]"))
+                      : launch_encode(gb::encode_direct_kernel<MODE, true, PITCHED, true>, grid, block, stream, Q, GB_KNAME("encode_direct_kernel[short launch]"));
+    return narrow ? launch_encode(gb::encode_direct_kernel<MODE, false, PITCHED, false>, grid, block, stream, Q, GB_KNAME("encode_direct_kernel"))
+                  : launch_encode(gb::encode_direct_kernel<MODE, true, PITCHED, false>, grid, block, stream, Q, GB_KNAME("encode_direct_kernel"));
 }
 
 template <int MODE, bool PITCHED>
 int launch_rows_grid(const gb::EncodeParams& Q, dim3 grid, dim3 block, cudaStream_t stream, bool narrow)
 {
     if (Q.firstWave != 0u || Q.prefetchNext != 0u)
-        return narrow ? launch_encode(gb::encode_rows_kernel<MODE, false, PITCHED, true>, grid, block, stream, Q)
-                      : launch_encode(gb::encode_rows_kernel<MODE, true, PITCHED, true>, grid, block, stream, Q);
-    return narrow ? launch_encode(gb::encode_rows_kernel<MODE, false, PITCHED, false>, grid, block, stream, Q)
-                  : launch_encode(gb::encode_rows_kernel<MODE, true, PITCHED, false>, grid, block, stream, Q);
+        return narrow ? launch_encode(gb::encode_rows_kernel<MODE, false, PITCHED, true>, grid, block, stream, Q, GB_KNAME("encode_rows_kernel[short launch]"))
+                      : launch_encode(gb::encode_rows_kernel<MODE, true, PITCHED, true>, grid, block, stream, Q, GB_KNAME("encode_rows_kernel[short launch]"));
+    return narrow ? launch_encode(gb::encode_rows_kernel<MODE, false, PITCHED, false>, grid, block, stream, Q, GB_KNAME("encode_rows_kernel"))
+                  : launch_encode(gb::encode_rows_kernel<MODE, true, PITCHED, false>, grid, block, stream, Q, GB_KNAME("encode_rows_kernel"));
 }
 
 int sm_count(int dev);
@@ -120,8 +125,8 @@ int launch_rows(const gb::EncodeParams& P, uint32_t nImages, cudaStream_t stream
         Q.prefetchNext = (pfNext && Q.firstWave != 0u) ? 1u : 0u;
         int rc;
         if (async)
-            rc = narrow ? launch_encode(gb::encode_rows_async_kernel<MODE, false>, grid, block, stream, Q)
-                        : launch_encode(gb::encode_rows_async_kernel<MODE, true>, grid, block, stream, Q);
+            rc = narrow ? launch_encode(gb::encode_rows_async_kernel<MODE, false>, grid, block, stream, Q, GB_KNAME("encode_rows_async_kernel"))
+                        : launch_encode(gb::encode_rows_async_kernel<MODE, true>, grid, block, stream, Q, GB_KNAME("encode_rows_async_kernel"));
         else if (nImages > 1u)
             rc = launch_rows_grid<MODE, true>(Q, grid, block, stream, narrow);
         else
@@ -320,6 +325,7 @@ int launch_tma_r(void* dst, void* dst2, const void* src, uint32_t width, uint32_
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
+        t_lastKernel = GB_KNAME("encode_tma_kernel");
         const cudaError_t e = cudaLaunchKernelEx(&cfg, gb::encode_tma_kernel<MODE, RB>, map, P);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (e != cudaSuccess) return cuda_rc(e);
@@ -437,6 +443,7 @@ int encode_floatref(int codec, void* dst, const void* src, uint32_t width, uint3
             Q.src += (uint64_t)img0 * srcPitch;
             Q.dst += (uint64_t)img0 * dstPitch;
             const dim3 grid(gx, (rows + ty - 1u) / ty, nz);
+            t_lastKernel = codec == GOOFY_B200_DXT1_FLOATREF ? "encode_floatref_kernel<dxt1>" : "encode_floatref_kernel<etc1s>";
             if (codec == GOOFY_B200_DXT1_FLOATREF) gb::encode_floatref_kernel<gb::kDxt1><<<grid, block, 0, stream>>>(Q);
             else gb::encode_floatref_kernel<gb::kEtc1><<<grid, block, 0, stream>>>(Q);
             g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -80,6 +80,9 @@ int goofy_b200_device_count(void);
 const char* goofy_b200_error_string(int code);
 /* Kernels launched by this library in the calling process so far (all threads, all devices). */
 uint64_t goofy_b200_kernel_launches(void);
+/* Name of the encode kernel the CALLING THREAD launched last through this library ("" before the first launch), e.g.
+ * "encode_direct_kernel<dxt1>" -- what a call actually ran, for benchmarks and profiles.  Static storage. */
+const char* goofy_b200_last_launch_kernel(void);
 /* Sets of host-path scratch (streams, device strips, pinned staging strips, descriptor arena) created in this process
  * so far.  A host thread leases one set while it lives and returns it to a pool when it exits, so this number tracks
  * the largest number of threads that were inside the host-pointer / batch entry points at the same time, not the
