@@ -6,15 +6,24 @@
 // MP/s = w*h / seconds / 1e6 (:953-958), RGB-PSNR with the 768 peak (:444,:466) -- and adds what
 // the reference does not have: device-resident batches, a multi-GPU shard scheduler (one host
 // thread and one stream per device, static partition by texture, no collectives) and CUDA-event
-// timing.  File writers, competitor encoders and the PNG loader of the reference harness are
-// out of scope.
+// timing.  With --images it is the reference's per-image loop (runTest, Src/main.cpp:836-986, and the image list
+// :991-1039): PNG ingest under the reference loader's contract (include/goofy_png.h), best-of-N timing of the
+// drop-in host call, device-resident timing, RGB-PSNR through the GPU decoder, a CSV row per encoder and image in the
+// reference's column order, and -- when the compiled reference is at hand (oracle/_ref/libgoofy_ref.so, dlopen'ed,
+// never linked) -- the SSE2 CPU path timed in the same run, single thread as shipped and row-parallel over T threads,
+// with the B200 bytes compared against it.  Competitor encoders, the RGB565 baseline and the TGA writers of the
+// reference harness are out of scope.
 //
 // CUDA C++ (the synthetic-texture generator is a kernel): built by Src/Makefile with
 //   nvcc -x cu -gencode arch=compute_100a,code=sm_100a -Iinclude Src/main.cpp -Lgoofy_b200 -lgoofy_b200
 //
-//   goofy_bench [--codec dxt1|etc1|both] [--size 8192] [--images 4] [--gpus N] [--iters 20]
-//               [--stride-pad 0] [--host-iters 3]
+//   goofy_bench [--codec dxt1|etc1|both] [--size 8192] [--textures 4] [--gpus N] [--iters 20]
+//               [--stride-pad 0] [--host-iters 3]                                  synthetic textures
+//   goofy_bench --images DIR [--list a,b,c] [--host-iters 128] [--iters 200] [--csv FILE] [--cpu-ref LIB.so] [--save-dir DIR]
+//                                                                                  the reference's image list
 #include <cuda_runtime.h>
+#include <dirent.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -28,7 +37,9 @@
 #include <thread>
 #include <vector>
 
-#include "goofy_tc.h"  // include/goofy_tc.h: goofy::compressDXT1/ETC1 + goofy::b200::*
+#include "goofy_containers.h"  // DDS / KTX writers (saveDds / saveKtx of the reference harness)
+#include "goofy_png.h"         // PNG ingest under the reference loader's contract
+#include "goofy_tc.h"          // include/goofy_tc.h: goofy::compressDXT1/ETC1 + goofy::b200::*
 
 typedef int (*CompressFunc_t)(unsigned char* result, const unsigned char* input, unsigned int width, unsigned int height,
                               unsigned int stride);
@@ -84,6 +95,9 @@ struct Options {
     std::string codec = "both";
     uint32_t size = 8192, images = 4, iters = 20, stridePad = 0, hostIters = 3;
     int gpus = 1;
+    // image-list mode
+    std::string imageDir, list, csv, cpuRef, saveDir;
+    bool hostItersGiven = false, itersGiven = false;
 };
 
 struct Shard {
@@ -106,18 +120,222 @@ static Options parse(int argc, char** argv)
         const std::string a = argv[i];
         if (a == "--codec") o.codec = next();
         else if (a == "--size") o.size = (uint32_t)std::atoi(next());
-        else if (a == "--images") o.images = (uint32_t)std::atoi(next());
+        else if (a == "--textures") o.images = (uint32_t)std::atoi(next());
+        else if (a == "--images") {   // a number: texture count of the synthetic mode (round-1 spelling); otherwise a directory of PNGs
+            const char* v = next();
+            if (*v && std::strspn(v, "0123456789") == std::strlen(v)) o.images = (uint32_t)std::atoi(v);
+            else o.imageDir = v;
+        }
+        else if (a == "--list") o.list = next();
+        else if (a == "--csv") o.csv = next();
+        else if (a == "--cpu-ref") o.cpuRef = next();
+        else if (a == "--save-dir") o.saveDir = next();
         else if (a == "--gpus") o.gpus = std::atoi(next());
-        else if (a == "--iters") o.iters = (uint32_t)std::atoi(next());
+        else if (a == "--iters") { o.iters = (uint32_t)std::atoi(next()); o.itersGiven = true; }
         else if (a == "--stride-pad") o.stridePad = (uint32_t)std::atoi(next());
-        else if (a == "--host-iters") o.hostIters = (uint32_t)std::atoi(next());
+        else if (a == "--host-iters") { o.hostIters = (uint32_t)std::atoi(next()); o.hostItersGiven = true; }
         else {
-            std::fprintf(stderr, "usage: goofy_bench [--codec dxt1|etc1|both] [--size N] [--images K] [--gpus G] [--iters I] "
-                                 "[--stride-pad BYTES] [--host-iters I]\n");
+            std::fprintf(stderr, "usage: goofy_bench [--codec dxt1|etc1|both] [--size N] [--textures K] [--gpus G] [--iters I] "
+                                 "[--stride-pad BYTES] [--host-iters I]\n"
+                                 "       goofy_bench --images DIR [--list a,b,c] [--host-iters 128] [--iters 200] [--csv FILE] [--cpu-ref LIB.so] "
+                                 "[--save-dir DIR]\n");
             std::exit(1);
         }
     }
     return o;
+}
+
+
+// ================================================================================ image-list mode
+// The compiled reference (oracle/_ref/libgoofy_ref.so: goofy::compress* behind oracle/ref_shim.cpp), loaded at run time
+// if it is there.  It is the timed CPU baseline and the byte-for-byte checker of this mode; the encoders never see it.
+struct CpuReference {
+    typedef int (*Fn)(unsigned char*, const unsigned char*, unsigned, unsigned, unsigned);
+    typedef int (*FnMt)(int, unsigned char*, const unsigned char*, unsigned, unsigned, unsigned, int);
+    void* handle = nullptr;
+    Fn single[2] = {nullptr, nullptr};
+    FnMt parallel = nullptr;
+    unsigned threads = 1;
+    bool open(const std::string& path)
+    {
+        handle = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!handle) return false;
+        single[0] = (Fn)dlsym(handle, "ref_goofy_compress_dxt1");
+        single[1] = (Fn)dlsym(handle, "ref_goofy_compress_etc1");
+        parallel = (FnMt)dlsym(handle, "ref_goofy_compress_mt");
+        unsigned (*hw)() = (unsigned (*)())dlsym(handle, "ref_hardware_threads");
+        if (hw) threads = std::max(1u, hw());
+        return single[0] && single[1] && parallel;
+    }
+};
+
+template <typename F>
+static double bestOfMicros(uint32_t iters, F fn)   // the reference's protocol: best of N calls (Src/main.cpp:653-664)
+{
+    double best = 1e30;
+    for (uint32_t k = 0; k < iters; ++k) {
+        const auto a = std::chrono::steady_clock::now();
+        fn();
+        best = std::min(best, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a).count());
+    }
+    return best;
+}
+
+static std::string exeDir(const char* argv0)
+{
+    std::string p = argv0;
+    const size_t slash = p.rfind('/');
+    return slash == std::string::npos ? "." : p.substr(0, slash);
+}
+
+static int runImageList(const Options& opt, const char* argv0)
+{
+    // the list: --list a,b,c, else every *.png of the directory in name order
+    std::vector<std::string> names;
+    if (!opt.list.empty()) {
+        size_t pos = 0;
+        while (pos <= opt.list.size()) {
+            const size_t comma = opt.list.find(',', pos);
+            const std::string n = opt.list.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+            if (!n.empty()) names.push_back(n);
+            if (comma == std::string::npos) break;
+            pos = comma + 1;
+        }
+    } else {
+        DIR* d = opendir(opt.imageDir.c_str());
+        if (!d) { std::fprintf(stderr, "cannot open directory %s\n", opt.imageDir.c_str()); return 1; }
+        while (dirent* e = readdir(d)) {
+            const std::string n = e->d_name;
+            if (n.size() > 4 && n.substr(n.size() - 4) == ".png") names.push_back(n.substr(0, n.size() - 4));
+        }
+        closedir(d);
+        std::sort(names.begin(), names.end());
+    }
+    CpuReference cpu;
+    const std::string refPath = opt.cpuRef.empty() ? exeDir(argv0) + "/../oracle/_ref/libgoofy_ref.so" : opt.cpuRef;
+    const bool haveCpu = cpu.open(refPath);
+    const uint32_t hostIters = opt.hostItersGiven ? std::max(1u, opt.hostIters) : 128u;   // kNumberOfIterations, Src/main.cpp:43
+    const uint32_t devIters = opt.itersGiven ? std::max(1u, opt.iters) : 200u;
+    FILE* csv = opt.csv.empty() ? nullptr : std::fopen(opt.csv.c_str(), "w");
+    auto row = [&](const char* image, const char* encoder, const char* format, double pixels, double micros, double psnr768, double psnrText,
+                   const char* exact) {
+        // the reference's column order (Src/main.cpp:948-962): image;encoder;format;pixels;microseconds;MP/s;quality...
+        char line[512];
+        std::snprintf(line, sizeof(line), "%s;%s;%s;%3.0f;%3.1f;%3.5f;%3.5f;%3.5f;%s\n", image, encoder, format, pixels, micros,
+                      micros > 0 ? pixels / micros : 0.0, psnr768, psnrText, exact);
+        std::fputs(line, stdout);
+        if (csv) std::fputs(line, csv);
+    };
+    std::printf("image;encoder;format;pixels;best_us;MP/s;psnrRGB(768 peak);psnr(textbook);bit_exact_vs_sse2\n");
+    if (csv) std::fprintf(csv, "image;encoder;format;pixels;best_us;MP/s;psnrRGB(768 peak);psnr(textbook);bit_exact_vs_sse2\n");
+
+    CK(cudaSetDevice(0));
+    cudaStream_t stream;
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    uint64_t* dSse;
+    CK(cudaMalloc(&dSse, 3 * sizeof(uint64_t)));
+    const char* formats[2] = {"DXT1", "ETC1"};
+    const CompressFunc_t fns[2] = {goofy::compressDXT1, goofy::compressETC1};
+    // sums for the closing summary: [codec][0 host call, 1 device, 2 cpu 1T, 3 cpu NT] MP/s, PSNR
+    double sumMps[2][4] = {}, sumPsnr[2] = {}, sumPsnrKodak[2] = {};
+    uint32_t loaded = 0, kodak = 0, skipped = 0, mismatches = 0;
+    for (const std::string& name : names) {
+        const std::string path = opt.imageDir + "/" + name + ".png";
+        goofy::png::Image im = goofy::png::load(path.c_str());
+        if (!im.error.empty()) {
+            std::fprintf(stderr, "%s: %s\n", path.c_str(), im.error.c_str());   // the reference harness skips such images too
+            ++skipped;
+            continue;
+        }
+        const uint32_t W = im.width, H = im.height, stride = W * 4;
+        const size_t inBytes = (size_t)stride * H, outBytes = (size_t)W * H / 2;
+        const double px = (double)W * H;
+        unsigned char* result = (unsigned char*)std::aligned_alloc(64, (outBytes + 63) / 64 * 64);
+        unsigned char* cpuResult = (unsigned char*)std::aligned_alloc(64, (outBytes + 63) / 64 * 64);
+        uint8_t *dSrc, *dDst;
+        CK(cudaMalloc(&dSrc, inBytes));
+        CK(cudaMalloc(&dDst, outBytes));
+        CK(cudaMemcpy(dSrc, im.rgba, inBytes, cudaMemcpyHostToDevice));
+        const bool isKodak = name.compare(0, 5, "kodim") == 0;
+        for (int c = 0; c < 2; ++c) {
+            if ((c == 0 && opt.codec == "etc1") || (c == 1 && opt.codec == "dxt1")) continue;
+            // the drop-in host call on ordinary (malloc'ed, 64-byte aligned) buffers, as the reference harness times it
+            GK(fns[c](result, im.rgba, W, H, stride));
+            const double hostUs = bestOfMicros(hostIters, [&] { GK(fns[c](result, im.rgba, W, H, stride)); });
+            // device-resident: back-to-back launches between two events
+            for (int k = 0; k < 5; ++k) GK(goofy::b200::encode((goofy::b200::Codec)c, dDst, dSrc, W, H, stride, stream));
+            float ms = 0, bestMs = 1e30f;
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaEventRecord(e0, stream));
+                for (uint32_t k = 0; k < devIters; ++k) GK(goofy::b200::encode((goofy::b200::Codec)c, dDst, dSrc, W, H, stride, stream));
+                CK(cudaEventRecord(e1, stream));
+                CK(cudaStreamSynchronize(stream));
+                CK(cudaEventElapsedTime(&ms, e0, e1));
+                bestMs = std::min(bestMs, ms);
+            }
+            const double devUs = bestMs * 1e3 / devIters;
+            // quality: decode + squared error on the device (goofy::b200::blockSse), the harness's psnrRGB formula (:444,:466)
+            uint64_t sse[3];
+            CK(cudaMemsetAsync(dSse, 0, sizeof(sse), stream));
+            GK(goofy::b200::blockSse((goofy::b200::Codec)c, dDst, dSrc, W, H, stride, dSse, stream));
+            CK(cudaMemcpyAsync(sse, dSse, sizeof(sse), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            const double mseSum = (double)(sse[0] + sse[1] + sse[2]) / px;
+            const double psnr768 = mseSum > 0 ? 10.0 * std::log10(768.0 * 768.0 / mseSum) : 999.0;
+            const double psnrText = mseSum > 0 ? 10.0 * std::log10(255.0 * 255.0 / (mseSum / 3.0)) : 999.0;
+            const char* exact = "n/a";
+            double cpu1 = 0, cpuN = 0;
+            if (haveCpu) {
+                cpu.single[c](cpuResult, im.rgba, W, H, stride);
+                exact = std::memcmp(cpuResult, result, outBytes) == 0 ? "yes" : "NO";
+                if (exact[0] == 'N') ++mismatches;
+                cpu1 = bestOfMicros(hostIters, [&] { cpu.single[c](cpuResult, im.rgba, W, H, stride); });
+                cpuN = bestOfMicros(std::max(8u, hostIters / 4), [&] { cpu.parallel(c, cpuResult, im.rgba, W, H, stride, (int)cpu.threads); });
+            }
+            row(name.c_str(), "b200_goofy (host call)", formats[c], px, hostUs, psnr768, psnrText, exact);
+            row(name.c_str(), "b200_goofy (device-resident)", formats[c], px, devUs, psnr768, psnrText, exact);
+            if (haveCpu) {
+                row(name.c_str(), "simd_goofy (cpu, 1 thread)", formats[c], px, cpu1, psnr768, psnrText, "reference");
+                char enc[64];
+                std::snprintf(enc, sizeof(enc), "simd_goofy (cpu, %u threads)", cpu.threads);
+                row(name.c_str(), enc, formats[c], px, cpuN, psnr768, psnrText, "reference");
+            }
+            sumMps[c][0] += px / hostUs;
+            sumMps[c][1] += px / devUs;
+            if (haveCpu) { sumMps[c][2] += px / cpu1; sumMps[c][3] += px / cpuN; }
+            sumPsnr[c] += psnr768;
+            if (isKodak) sumPsnrKodak[c] += psnr768;
+            if (!opt.saveDir.empty()) {   // saveDds / saveKtx of the reference harness (:154-220)
+                const std::string out = opt.saveDir + "/" + name + (c == 0 ? ".dds" : ".ktx");
+                const bool ok = c == 0 ? goofy::containers::writeDdsDxt1(out.c_str(), result, W, H) : goofy::containers::writeKtxEtc1(out.c_str(), result, W, H);
+                if (!ok) std::fprintf(stderr, "cannot write %s\n", out.c_str());
+            }
+        }
+        ++loaded;
+        if (isKodak) ++kodak;
+        CK(cudaFree(dSrc));
+        CK(cudaFree(dDst));
+        std::free(result);
+        std::free(cpuResult);
+        goofy::png::freeImage(im);
+    }
+    if (csv) std::fclose(csv);
+    std::printf("{\"harness\": \"Src/main.cpp --images\", \"images\": %u, \"skipped\": %u, \"host_iters\": %u, \"device_iters\": %u, \"cpu_reference\": %s, "
+                "\"cpu_threads\": %u, \"mismatches_vs_sse2\": %u",
+                loaded, skipped, hostIters, devIters, haveCpu ? "true" : "false", haveCpu ? cpu.threads : 0u, mismatches);
+    const char* names2[2] = {"dxt1", "etc1"};
+    for (int c = 0; c < 2; ++c) {
+        if (loaded == 0 || sumMps[c][0] == 0) continue;
+        std::printf(", \"%s\": {\"mean_mp_per_s_host_call\": %.1f, \"mean_mp_per_s_device\": %.1f, \"mean_mp_per_s_cpu_1_thread\": %.1f, "
+                    "\"mean_mp_per_s_cpu_all_threads\": %.1f, \"mean_psnr_rgb768\": %.3f, \"kodak_images\": %u, \"kodak_mean_psnr_rgb768\": %.3f}",
+                    names2[c], sumMps[c][0] / loaded, sumMps[c][1] / loaded, sumMps[c][2] / loaded, sumMps[c][3] / loaded, sumPsnr[c] / loaded, kodak,
+                    kodak ? sumPsnrKodak[c] / kodak : 0.0);
+    }
+    std::printf("}\n");
+    return mismatches ? 5 : (loaded ? 0 : 6);
 }
 
 int main(int argc, char** argv)
@@ -128,6 +346,7 @@ int main(int argc, char** argv)
         std::fprintf(stderr, "no CUDA device: the encoders have no CPU fallback\n");
         return 4;
     }
+    if (!opt.imageDir.empty()) return runImageList(opt, argv[0]);
     const int G = std::min(opt.gpus, visible);
     const uint32_t W = opt.size, H = opt.size, stride = W * 4 + opt.stridePad;
     const size_t imgBytes = (size_t)stride * H, outBytes = (size_t)W * H / 2;

@@ -60,7 +60,8 @@ def read_dds(path):
 
 def ktx_bytes(blocks, width: int, height: int, gl_internal_format: int = GL_ETC1_RGB8_OES) -> bytes:
     data = _payload(blocks, width, height)
-    base = GL_RGB if gl_internal_format in (GL_ETC1_RGB8_OES, GL_COMPRESSED_RGB_S3TC_DXT1_EXT) else GL_RGBA
+    # the reference's rule (saveKtx, Src/main.cpp:199): GL_RGB for ETC1 only, GL_RGBA for every other format
+    base = GL_RGB if gl_internal_format == GL_ETC1_RGB8_OES else GL_RGBA
     header = KTX_IDENTIFIER + struct.pack("<13I", KTX_ENDIANNESS, 0, 1, 0, gl_internal_format, base, width, height,
                                           0, 0, 1, 1, 0)
     assert len(header) == 64

@@ -96,3 +96,13 @@ def test_png_ingest_contract(tmp_path):
         containers.load_png_rgba(tmp_path / "w.png")
     with pytest.raises(ValueError):
         containers.load_png_rgba(tmp_path / "h.png")
+
+
+def test_ktx_base_internal_format_follows_the_reference_rule():
+    """saveKtx (Src/main.cpp:199 of the reference): glBaseInternalFormat is GL_RGB for ETC1 and GL_RGBA otherwise."""
+    import struct
+    blocks = np.zeros(16 * 16 // 2, dtype=np.uint8)
+    etc = containers.ktx_bytes(blocks, 16, 16)
+    dxt = containers.ktx_bytes(blocks, 16, 16, containers.GL_COMPRESSED_RGB_S3TC_DXT1_EXT)
+    assert struct.unpack_from("<I", etc, 12 + 5 * 4)[0] == containers.GL_RGB
+    assert struct.unpack_from("<I", dxt, 12 + 5 * 4)[0] == containers.GL_RGBA
