@@ -145,13 +145,17 @@ int goofy_b200_encode_relaxed_device(int codec, void* d_result, const void* d_in
     if (!d_result || !d_input) return GOOFY_B200_E_NULL;
     if (((uintptr_t)d_input & 3u) != 0u || (stride & 3u) != 0u || ((uintptr_t)d_result & 7u) != 0u) return GOOFY_B200_E_ALIGN;
     const uint32_t bw = (width + 3u) / 4u, bh = (height + 3u) / 4u;
-    if (bh > 65535u) return GOOFY_B200_E_ARGS;
     int rc = ensure_device_ready();
     if (rc != GOOFY_B200_OK) return rc;
-    const dim3 grid((bw + 255u) / 256u, bh, 1);
+    // DXT1 flavours: one block row per CTA; ETC1s flavours: four (their CTAs stage the control table first)
+    const bool etc = codec == GOOFY_B200_ETC1 || codec == GOOFY_B200_ETC1_FLOATREF;
+    uint32_t gy = etc ? (bh + 3u) / 4u : bh;
+    if (gy > 65535u) gy = 65535u;   // taller images: every CTA simply walks further
+    const dim3 grid((bw + 255u) / 256u, gy, 1);
     cudaStream_t s = (cudaStream_t)stream;
     const uint8_t* src = (const uint8_t*)d_input;
     uint8_t* dst = (uint8_t*)d_result;
+    t_lastKernel = "encode_relaxed_kernel";
     switch (codec) {
         case GOOFY_B200_DXT1: gb::encode_relaxed_kernel<gb::kDxt1, 0><<<grid, 256, 0, s>>>(src, dst, width, height, stride); break;
         case GOOFY_B200_ETC1: gb::encode_relaxed_kernel<gb::kEtc1, 0><<<grid, 256, 0, s>>>(src, dst, width, height, stride); break;

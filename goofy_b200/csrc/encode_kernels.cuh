@@ -41,6 +41,10 @@ enum Mode : int { kDxt1 = 0, kEtc1 = 1, kDual = 2 };
 #define GB_ASYNC_CTAS_SINGLE 5
 #endif
 #define GB_ASYNC_CTAS(mode) ((mode) == 2 ? GB_ASYNC_CTAS_DUAL : GB_ASYNC_CTAS_SINGLE)
+// Resident CTAs per SM of the row-walking ETC1s relaxed-shape kernel (5 -> 48 registers, no spills; 6 -> 40 registers, 24 bytes spilled)
+#ifndef GB_RELAXED_ETC1_CTAS
+#define GB_RELAXED_ETC1_CTAS 5
+#endif
 // Selector-gathering scheme of the DXT1 kernel (block_codec.cuh `Selectors`); -D overridable for A/B runs.
 // The ETC1s and dual-output kernels always use the flag-byte scheme.
 #ifndef GB_SEL_DXT1
@@ -341,10 +345,13 @@ __global__ void __launch_bounds__(GB_TPB, GB_ASYNC_CTAS(MODE)) encode_rows_async
     }
 }
 
-// Float-reference flavour (goofyRef::, block_codec.cuh "float-reference flavour"): one-shot CTAs,
-// any width that is a multiple of 4.  the control table is goofyRef's, by brightRange.
-template <int CODEC>
-__global__ void __launch_bounds__(256, 8) encode_floatref_kernel(const EncodeParams P)
+// Float-reference flavour (goofyRef::, block_codec.cuh "float-reference flavour"), any width that is a multiple of 4;
+// the control table is goofyRef's, by brightRange.  grid.z = image of a batch at fixed pitches.
+// ROWS = false: one-shot CTAs (what the DXT1 flavour runs: it is HBM-bound either way, like its SSE2-exact twin).
+// ROWS = true: every CTA walks down its image in steps of gridDim.y * blockDim.y block rows, so the control-table
+// staging and the index set-up are paid once per few blocks (the ETC1s flavour: 6.06 -> TB/s as one-shot CTAs, r01f).
+template <int CODEC, bool ROWS>
+__global__ void __launch_bounds__(256, CODEC == kDxt1 ? 8 : 6) encode_floatref_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[CODEC == kDxt1 ? 1 : 256];
     if (CODEC != kDxt1) {
@@ -352,72 +359,79 @@ __global__ void __launch_bounds__(256, 8) encode_floatref_kernel(const EncodePar
         __syncthreads();
     }
     const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t by = P.by0 + blockIdx.y * blockDim.y + threadIdx.y;
+    uint32_t by = P.by0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (bx >= P.bw || by >= P.bh) return;
-    const uint8_t* s = P.src + (uint64_t)blockIdx.z * P.srcPitch + (uint64_t)by * 4u * P.stride + (uint64_t)bx * 16u;
-    const uint4 r0 = load_row(s);
-    const uint4 r1 = load_row(s + P.stride);
-    const uint4 r2 = load_row(s + 2ull * P.stride);
-    const uint4 r3 = load_row(s + 3ull * P.stride);
-    const uint32_t p[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
-                            r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
-    // minimum brightness range: 8 for DXT1 (:667), 16 for ETC1S (:766), times 4
-    const RefFront f = analyse_ref(p, CODEC == kDxt1 ? 32u : 64u);
-    uint32_t w0, w1;
-    if (CODEC == kDxt1) encode_dxt1_ref(p, f, w0, w1);
-    else encode_etc1_ref(p, f, lut, w0, w1);
-    store_block(P.dst + (uint64_t)blockIdx.z * P.dstPitch + ((uint64_t)by * P.bw + bx) * 8u, w0, w1);
+    const uint8_t* src = P.src + (uint64_t)blockIdx.z * P.srcPitch + (uint64_t)bx * 16u;
+    uint8_t* dst = P.dst + (uint64_t)blockIdx.z * P.dstPitch + (uint64_t)bx * 8u;
+#pragma unroll 1
+    do {
+        const uint8_t* s = src + (uint64_t)by * 4u * P.stride;
+        const uint4 r0 = load_row(s);
+        const uint4 r1 = load_row(s + P.stride);
+        const uint4 r2 = load_row(s + 2ull * P.stride);
+        const uint4 r3 = load_row(s + 3ull * P.stride);
+        encode_and_store_flavour<CODEC, 1>(r0, r1, r2, r3, lut, dst + (uint64_t)by * P.bw * 8u, nullptr);
+    } while (ROWS && (by += gridDim.y * blockDim.y) < P.bh);
 }
 
 // Relaxed shapes: any width / height >= 1 and any 4-byte-aligned stride.  Blocks that
 // hang over the right or bottom edge replicate the last column / row (clamp-to-edge), so the output has
 // ceil(w/4) x ceil(h/4) blocks.  Blocks that lie wholly inside the image take the four 128-bit row loads of the
 // strict kernels when the rows are 16-byte aligned (a uniform condition); edge blocks and unaligned images take
-// sixteen clamped 32-bit loads.  FLAVOUR 0 = SSE2-exact arithmetic, 1 = float-reference arithmetic; on images the
+// sixteen clamped 32-bit loads.  The DXT1 flavours are launched as one-shot CTAs (grid.y = block rows), the ETC1s
+// flavours with CTAs that walk four block rows each.  FLAVOUR 0 = SSE2-exact arithmetic, 1 = float-reference arithmetic; on images the
 // strict entry points accept, the bytes are the same.
 template <int CODEC, int FLAVOUR>
-__global__ void __launch_bounds__(256, 6) encode_relaxed_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                             uint32_t width, uint32_t height, uint32_t stride)
+__global__ void __launch_bounds__(256, CODEC == kDxt1 ? 6 : GB_RELAXED_ETC1_CTAS) encode_relaxed_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                                  uint32_t width, uint32_t height, uint32_t stride)
 {
+    constexpr bool ROWS = CODEC != kDxt1;   // DXT1 flavours: one-shot CTAs (gridDim.y = block rows)
     __shared__ uint32_t lut[CODEC == kDxt1 ? 1 : 256];
     if (CODEC != kDxt1) {
         stage_control_lut<FLAVOUR != 0, 256>(lut, threadIdx.x);
         __syncthreads();
     }
     const uint32_t bw = (width + 3u) / 4u, bh = (height + 3u) / 4u;
-    const uint32_t bx = blockIdx.x * 256u + threadIdx.x, by = blockIdx.y;
-    if (bx >= bw || by >= bh) return;
-    uint32_t p[16];
+    const uint32_t bx = blockIdx.x * 256u + threadIdx.x;
+    if (bx >= bw) return;
     const bool aligned = ((reinterpret_cast<uintptr_t>(src) | stride) & 15u) == 0u;
-    if (aligned && bx * 4u + 3u < width && by * 4u + 3u < height) {
-        const uint8_t* s = src + (uint64_t)by * 4u * stride + (uint64_t)bx * 16u;
-        const uint4 r0 = load_row(s), r1 = load_row(s + stride), r2 = load_row(s + 2ull * stride), r3 = load_row(s + 3ull * stride);
-        p[0] = r0.x; p[1] = r0.y; p[2] = r0.z; p[3] = r0.w;
-        p[4] = r1.x; p[5] = r1.y; p[6] = r1.z; p[7] = r1.w;
-        p[8] = r2.x; p[9] = r2.y; p[10] = r2.z; p[11] = r2.w;
-        p[12] = r3.x; p[13] = r3.y; p[14] = r3.z; p[15] = r3.w;
-    } else {
+    const bool insideX = bx * 4u + 3u < width;
+    // CTAs walk down the image (gridDim.y apart): the table staging and the column tests are paid once per few blocks
+    uint32_t by = blockIdx.y;
+    if (by >= bh) return;
+#pragma unroll 1
+    do {
+        uint32_t p[16];
+        if (aligned && insideX && by * 4u + 3u < height) {
+            const uint8_t* s = src + (uint64_t)by * 4u * stride + (uint64_t)bx * 16u;
+            const uint4 r0 = load_row(s), r1 = load_row(s + stride), r2 = load_row(s + 2ull * stride), r3 = load_row(s + 3ull * stride);
+            p[0] = r0.x; p[1] = r0.y; p[2] = r0.z; p[3] = r0.w;
+            p[4] = r1.x; p[5] = r1.y; p[6] = r1.z; p[7] = r1.w;
+            p[8] = r2.x; p[9] = r2.y; p[10] = r2.z; p[11] = r2.w;
+            p[12] = r3.x; p[13] = r3.y; p[14] = r3.z; p[15] = r3.w;
+        } else {
 #pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            const uint32_t row = min(by * 4u + (uint32_t)y, height - 1u);
+            for (int y = 0; y < 4; ++y) {
+                const uint32_t row = min(by * 4u + (uint32_t)y, height - 1u);
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const uint32_t col = min(bx * 4u + (uint32_t)x, width - 1u);
-                p[4 * y + x] = __ldg(reinterpret_cast<const uint32_t*>(src + (uint64_t)row * stride + (uint64_t)col * 4u));
+                for (int x = 0; x < 4; ++x) {
+                    const uint32_t col = min(bx * 4u + (uint32_t)x, width - 1u);
+                    p[4 * y + x] = __ldg(reinterpret_cast<const uint32_t*>(src + (uint64_t)row * stride + (uint64_t)col * 4u));
+                }
             }
         }
-    }
-    uint32_t w0, w1;
-    if (FLAVOUR == 0) {
-        const BlockFront f = analyse(p);
-        if (CODEC == kDxt1) encode_dxt1<GB_SEL_DXT1>(p, f, w0, w1);
-        else encode_etc1(p, f, lut, w0, w1);
-    } else {
-        const RefFront f = analyse_ref(p, CODEC == kDxt1 ? 32u : 64u);
-        if (CODEC == kDxt1) encode_dxt1_ref(p, f, w0, w1);
-        else encode_etc1_ref(p, f, lut, w0, w1);
-    }
-    store_block(dst + ((uint64_t)by * bw + bx) * 8u, w0, w1);
+        uint32_t w0, w1;
+        if (FLAVOUR == 0) {
+            const BlockFront f = analyse(p);
+            if (CODEC == kDxt1) encode_dxt1<GB_SEL_DXT1>(p, f, w0, w1);
+            else encode_etc1(p, f, lut, w0, w1);
+        } else {
+            const RefFront f = analyse_ref(p, CODEC == kDxt1 ? 32u : 64u);
+            if (CODEC == kDxt1) encode_dxt1_ref(p, f, w0, w1);
+            else encode_etc1_ref(p, f, lut, w0, w1);
+        }
+        store_block(dst + ((uint64_t)by * bw + bx) * 8u, w0, w1);
+    } while (ROWS && (by += gridDim.y) < bh);
 }
 
 // ------------------------------------------------------------------ ragged batches

@@ -433,7 +433,25 @@ int encode_floatref(int codec, void* dst, const void* src, uint32_t width, uint3
     while (tx < 256u && tx < P.bw) tx <<= 1;
     const uint32_t ty = 256u / tx;
     const dim3 block(tx, ty, 1);
-    const uint32_t gx = (P.bw + tx - 1u) / tx, rowsPerLaunch = 65535u * ty;
+    const uint32_t gx = (P.bw + tx - 1u) / tx, rowGroups = (P.bh + ty - 1u) / ty;
+    if (codec == GOOFY_B200_ETC1_FLOATREF) {
+        // row-walking CTAs, four block rows each (the ETC1s flavour pays a table staging and a barrier per CTA)
+        uint32_t gy = (rowGroups + 3u) / 4u;
+        if (gy > 65535u) gy = 65535u;
+        for (uint32_t img0 = 0; img0 < nImages; img0 += 65535u) {
+            const uint32_t nz = nImages - img0 < 65535u ? nImages - img0 : 65535u;
+            gb::EncodeParams Q = P;
+            Q.by0 = 0;
+            Q.src += (uint64_t)img0 * srcPitch;
+            Q.dst += (uint64_t)img0 * dstPitch;
+            t_lastKernel = "encode_floatref_kernel<etc1s, row-walking>";
+            gb::encode_floatref_kernel<gb::kEtc1, true><<<dim3(gx, gy, nz), block, 0, stream>>>(Q);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            GB_CUDA(cudaGetLastError());
+        }
+        return GOOFY_B200_OK;
+    }
+    const uint32_t rowsPerLaunch = 65535u * ty;
     for (uint32_t img0 = 0; img0 < nImages; img0 += 65535u) {
         const uint32_t nz = nImages - img0 < 65535u ? nImages - img0 : 65535u;
         for (uint32_t by0 = 0; by0 < P.bh; by0 += rowsPerLaunch) {
@@ -443,9 +461,8 @@ int encode_floatref(int codec, void* dst, const void* src, uint32_t width, uint3
             Q.src += (uint64_t)img0 * srcPitch;
             Q.dst += (uint64_t)img0 * dstPitch;
             const dim3 grid(gx, (rows + ty - 1u) / ty, nz);
-            t_lastKernel = codec == GOOFY_B200_DXT1_FLOATREF ? "encode_floatref_kernel<dxt1>" : "encode_floatref_kernel<etc1s>";
-            if (codec == GOOFY_B200_DXT1_FLOATREF) gb::encode_floatref_kernel<gb::kDxt1><<<grid, block, 0, stream>>>(Q);
-            else gb::encode_floatref_kernel<gb::kEtc1><<<grid, block, 0, stream>>>(Q);
+            t_lastKernel = "encode_floatref_kernel<dxt1>";
+            gb::encode_floatref_kernel<gb::kDxt1, false><<<grid, block, 0, stream>>>(Q);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             GB_CUDA(cudaGetLastError());
         }
