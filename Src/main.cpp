@@ -221,7 +221,7 @@ static int runImageList(const Options& opt, const char* argv0)
                    const char* exact) {
         // the reference's column order (Src/main.cpp:948-962): image;encoder;format;pixels;microseconds;MP/s;quality...
         char line[512];
-        std::snprintf(line, sizeof(line), "%s;%s;%s;%3.0f;%3.1f;%3.5f;%3.5f;%3.5f;%s\n", image, encoder, format, pixels, micros,
+        std::snprintf(line, sizeof(line), "%s;%s;%s;%3.0f;%3.2f;%3.5f;%3.5f;%3.5f;%s\n", image, encoder, format, pixels, micros,
                       micros > 0 ? pixels / micros : 0.0, psnr768, psnrText, exact);
         std::fputs(line, stdout);
         if (csv) std::fputs(line, csv);

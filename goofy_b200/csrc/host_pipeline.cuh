@@ -26,7 +26,32 @@ bool is_pageable(const void* p)
     return pageable;
 }
 
-constexpr size_t kStagePieceBytes = 384u << 10;   // smallest piece of a strip staged and sent on its own
+constexpr size_t kStagePieceBytes = 768u << 10;   // zero-copy path: smallest piece of a strip staged and encoded on its own
+constexpr size_t kCopyPieceBytes = 2u << 20;      // copying path: smallest piece of a strip staged and sent on its own
+
+// GOOFY_B200_TRACE_HOST=n: the n-th host-pointer call of a thread prints where its time went (microseconds since the
+// call started, to stderr).  Diagnostic for the small-image path (profiles/r02_hostlat_*.txt); costs one branch otherwise.
+struct HostTrace {
+    static int wanted() { static const int n = env_int("GOOFY_B200_TRACE_HOST", 1, 1 << 30, 0); return n; }
+    std::chrono::steady_clock::time_point t0;
+    struct Mark { const char* what; double us; };
+    Mark marks[64];
+    int n = 0;
+    bool on = false;
+    void begin(bool enable) { on = enable; n = 0; if (on) t0 = std::chrono::steady_clock::now(); }
+    void mark(const char* what)
+    {
+        if (on && n < 64) marks[n++] = Mark{what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count()};
+    }
+    void end()
+    {
+        if (!on) return;
+        for (int i = 0; i < n; ++i) std::fprintf(stderr, "[goofy_b200 host trace] %8.1f us  %s\n", marks[i].us, marks[i].what);
+        on = false;
+    }
+};
+thread_local HostTrace t_trace;
+thread_local int t_hostCalls = 0;
 
 // One host image of a host-pointer call, validated and cut into strips.
 struct HostJob {
@@ -101,8 +126,10 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         if ((J.stageOut || J.stageOut2) && out > needStageOut) needStageOut = out;
     }
     if (needIn == 0) return GOOFY_B200_OK;
+    t_trace.begin(HostTrace::wanted() != 0 && ++t_hostCalls == HostTrace::wanted());
     ThreadResources& R = thread_resources(dev);
     int rc = R.pipe.prepare(dev, needIn, needOut);
+    t_trace.mark("scratch ready");
     if (rc != GOOFY_B200_OK) return rc;
     if (needStageIn || needStageOut) {
         rc = R.stage.ensure(needStageIn, needStageOut);
@@ -114,6 +141,7 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         const HostJob* J = pending[slot].job;
         if (!J) return GOOFY_B200_OK;
         GB_CUDA(cudaStreamSynchronize(R.pipe.stream[slot]));
+        t_trace.mark("stream synchronised");
         if (J->stageOut)
             CopyPool::get().copy1d(J->result + (size_t)pending[slot].r0 * J->outRowBytes, (const uint8_t*)R.stage.out[slot],
                                    (size_t)pending[slot].rows * J->outRowBytes);
@@ -122,8 +150,73 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
                                    (const uint8_t*)R.stage.out[slot] + (size_t)J->stripRows * J->outRowBytes,
                                    (size_t)pending[slot].rows * J->outRowBytes);
         pending[slot].job = nullptr;
+        t_trace.mark("results copied out of the staging strip");
         return GOOFY_B200_OK;
     };
+    // The encode launch of one strip (or one piece of it): both codecs when the job has a second result.
+    auto launch = [&](const HostJob& J, uint8_t* out, uint8_t* out2, const uint8_t* in, uint32_t pixelRows, uint32_t stride, cudaStream_t s) -> int {
+        return J.result2 ? encode_uniform(gb::kDual, out, out2, in, J.width, pixelRows, stride, 0, 0, 1, s)
+                         : encode_any(codec, out, in, J.width, pixelRows, stride, 0, 0, 1, s);
+    };
+    // Small strips (a test-image-sized texture is ONE strip of 1.5 MiB) skip the copy engine altogether: the kernel reads
+    // the pinned input -- the caller's buffer, or the staging strip -- straight over PCIe and writes its blocks straight
+    // into the pinned result (or staging strip).  A 1.5 MiB H2D copy costs 38 us of which 8 are fixed, the 192 KiB D2H copy
+    // 14 us of which 10 are fixed, and every extra piece of a piecewise H2D pays the fixed part again (measured with
+    // GOOFY_B200_TRACE_HOST, profiles/r02_hostlat_768x512.txt); a kernel launch costs 3-4 us and pulls at link speed.
+    // Pageable input is staged in up to four pieces of whole block rows, each encoded by its own launch as soon as it is
+    // in pinned memory, so the link works on piece k while the copy threads stage piece k + 1.
+    auto issue_zero_copy = [&](int slot, const HostJob& J, uint32_t r0, uint32_t rows, bool& taken) -> int {
+        taken = false;
+        cudaStream_t s = R.pipe.stream[slot];
+        const uint8_t* src = J.input + (size_t)r0 * 4u * J.stride;
+        const size_t half = (size_t)J.stripRows * J.outRowBytes;
+        void* p = nullptr;
+        // device views of the three host buffers the kernel touches; any of them not mapped -> the copying path
+        const uint8_t* inDev = nullptr;
+        if (J.stageIn) {
+            if (cudaHostGetDevicePointer(&p, R.stage.in[slot], 0) != cudaSuccess) { cudaGetLastError(); return GOOFY_B200_OK; }
+            inDev = (const uint8_t*)p;
+        } else {
+            if (cudaHostGetDevicePointer(&p, const_cast<uint8_t*>(src), 0) != cudaSuccess) { cudaGetLastError(); return GOOFY_B200_OK; }
+            inDev = (const uint8_t*)p;
+        }
+        uint8_t *outDev = nullptr, *out2Dev = nullptr;
+        void* outHost = J.stageOut ? R.stage.out[slot] : (void*)(J.result + (size_t)r0 * J.outRowBytes);
+        if (cudaHostGetDevicePointer(&p, outHost, 0) != cudaSuccess) { cudaGetLastError(); return GOOFY_B200_OK; }
+        outDev = (uint8_t*)p;
+        if (J.result2) {
+            void* out2Host = J.stageOut2 ? (void*)((uint8_t*)R.stage.out[slot] + half) : (void*)(J.result2 + (size_t)r0 * J.outRowBytes);
+            if (cudaHostGetDevicePointer(&p, out2Host, 0) != cudaSuccess) { cudaGetLastError(); return GOOFY_B200_OK; }
+            out2Dev = (uint8_t*)p;
+        }
+        if ((((uintptr_t)outDev | (uintptr_t)out2Dev) & 7u) != 0u) return GOOFY_B200_OK;   // the kernels store 8-byte blocks
+        taken = true;
+        if (!J.stageIn) {
+            const int r = launch(J, outDev, out2Dev, inDev, rows * 4u, J.stride, s);
+            t_trace.mark("zero-copy kernel launched (pinned input)");
+            if (r != GOOFY_B200_OK) return r;
+        } else {
+            size_t pieces = (size_t)rows * 4u * J.rowBytes / kStagePieceBytes;
+            pieces = pieces < 1u ? 1u : (pieces > 4u ? 4u : pieces);
+            if (pieces > rows) pieces = rows;
+            for (size_t k = 0; k < pieces; ++k) {
+                const size_t b0 = (size_t)rows * k / pieces, b1 = (size_t)rows * (k + 1u) / pieces;   // block rows of this piece
+                uint8_t* stage = (uint8_t*)R.stage.in[slot] + b0 * 4u * J.rowBytes;
+                CopyPool::get().copy2d(stage, J.rowBytes, src + b0 * 4u * J.stride, J.stride, J.rowBytes, (b1 - b0) * 4u);
+                t_trace.mark("piece staged into pinned memory");
+                const int r = launch(J, outDev + b0 * J.outRowBytes, out2Dev ? out2Dev + b0 * J.outRowBytes : nullptr,
+                                     inDev + b0 * 4u * J.rowBytes, (uint32_t)(b1 - b0) * 4u, (uint32_t)J.rowBytes, s);
+                t_trace.mark("zero-copy kernel launched on the piece");
+                if (r != GOOFY_B200_OK) return r;
+            }
+        }
+        pending[slot].job = &J;
+        pending[slot].r0 = r0;
+        pending[slot].rows = rows;
+        return GOOFY_B200_OK;
+    };
+    static const size_t zeroCopyMax = (size_t)env_int("GOOFY_B200_ZEROCOPY_MAX_KB", 0, 1 << 22, 32768) << 10;
+    static const bool zeroCopyPageable = env_int("GOOFY_B200_ZEROCOPY_PAGEABLE", 0, 1, 1) != 0;
     // One strip: stage (if pageable) -> H2D -> kernel -> D2H, all on the slot's stream.
     auto issue = [&](int slot, const HostJob& J, uint32_t r0, uint32_t rows) -> int {
         cudaStream_t s = R.pipe.stream[slot];
@@ -133,31 +226,45 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
             const int r = retire(slot);
             if (r != GOOFY_B200_OK) return r;
         }
+        // decided per IMAGE.  Pinned input: up to 32 MiB (beyond that the copy engine's 53 GB/s beats the ~41 GB/s a kernel
+        // pulls over the link: 4096^2 1290 vs 1337 us, 8192^2 5000 vs 5284 us).  Pageable input: always -- the staging copy
+        // is the bottleneck there and one step fewer behind it wins at every size (768x512 99 -> 62 us, 2048^2 632 -> 428 us,
+        // 8192^2 5940 -> 5524 us; profiles/r02_hostlat_zero_copy.txt).
+        if (J.stageIn ? zeroCopyPageable : (size_t)J.blockRows * 4u * J.rowBytes <= zeroCopyMax) {
+            bool taken = false;
+            const int r = issue_zero_copy(slot, J, r0, rows, taken);
+            if (r != GOOFY_B200_OK || taken) return r;
+        }
         if (J.stageIn) {
             // staged in up to four pieces, each sent as soon as it is in pinned memory: the DMA of one piece runs under
-            // the staging copy of the next, which is most of what a call on a test-image-sized texture spends
+            // the staging copy of the next (pieces of 2 MiB and more: below that the fixed cost of a copy, about 8 us,
+            // outweighs the overlap)
             const size_t pixelRows = (size_t)rows * 4u;
-            size_t pieces = pixelRows * J.rowBytes / kStagePieceBytes;
+            size_t pieces = pixelRows * J.rowBytes / kCopyPieceBytes;
             pieces = pieces < 1u ? 1u : (pieces > 4u ? 4u : pieces);
             for (size_t k = 0; k < pieces; ++k) {
                 const size_t y0 = pixelRows * k / pieces, y1 = pixelRows * (k + 1u) / pieces;
                 uint8_t* stage = (uint8_t*)R.stage.in[slot] + y0 * J.rowBytes;
                 CopyPool::get().copy2d(stage, J.rowBytes, src + y0 * J.stride, J.stride, J.rowBytes, y1 - y0);
+                t_trace.mark("piece staged into pinned memory");
                 GB_CUDA(cudaMemcpyAsync((uint8_t*)R.pipe.dIn[slot] + y0 * J.rowBytes, stage, (y1 - y0) * J.rowBytes, cudaMemcpyHostToDevice, s));
+                t_trace.mark("piece H2D issued");
             }
         } else {
             GB_CUDA(cudaMemcpy2DAsync(R.pipe.dIn[slot], J.rowBytes, src, J.stride, J.rowBytes, (size_t)rows * 4u, cudaMemcpyHostToDevice, s));
+            t_trace.mark("H2D issued (pinned input)");
         }
         const size_t half = (size_t)J.stripRows * J.outRowBytes;   // where a dual-output job keeps its ETC1s blocks
         uint8_t* dOut = (uint8_t*)R.pipe.dOut[slot];
-        const int r = J.result2 ? encode_uniform(gb::kDual, dOut, dOut + half, R.pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s)
-                                : encode_any(codec, dOut, R.pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s);
+        const int r = launch(J, dOut, dOut + half, (const uint8_t*)R.pipe.dIn[slot], rows * 4u, (uint32_t)J.rowBytes, s);
         if (r != GOOFY_B200_OK) return r;
+        t_trace.mark("kernel launched");
         GB_CUDA(cudaMemcpyAsync(J.stageOut ? R.stage.out[slot] : (void*)(J.result + (size_t)r0 * J.outRowBytes), dOut,
                                 (size_t)rows * J.outRowBytes, cudaMemcpyDeviceToHost, s));
         if (J.result2)
             GB_CUDA(cudaMemcpyAsync(J.stageOut2 ? (void*)((uint8_t*)R.stage.out[slot] + half) : (void*)(J.result2 + (size_t)r0 * J.outRowBytes),
                                     dOut + half, (size_t)rows * J.outRowBytes, cudaMemcpyDeviceToHost, s));
+        t_trace.mark("D2H issued");
         pending[slot].job = &J;
         pending[slot].r0 = r0;
         pending[slot].rows = rows;
@@ -184,6 +291,8 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         rc = retire(slot);
         if (rc != GOOFY_B200_OK) return fail(rc);
     }
+    t_trace.mark("done");
+    t_trace.end();
     return GOOFY_B200_OK;
 }
 
