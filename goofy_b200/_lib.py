@@ -37,6 +37,10 @@ PROTOTYPES = {
     "goofy_b200_last_launch_kernel": (C.c_char_p, []),
     "goofy_b200_set_load_path": (_int, [_int]),
     "goofy_b200_get_load_path": (_int, []),
+    "goofy_b200_set_host_rgb_staging": (_int, [_int]),
+    "goofy_b200_get_host_rgb_staging": (_int, []),
+    "goofy_b200_host_threads": (_int, []),
+    "goofy_b200_host_link_stats": (None, [C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "goofy_b200_compress_dxt1": (_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_uint]),
     "goofy_b200_compress_etc1": (_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_uint]),
     "goofy_b200_compress_dxt1_floatref": (_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_uint]),
@@ -45,6 +49,7 @@ PROTOTYPES = {
     "goofy_b200_encode_dual_host": (_int, [_vp, _vp, _vp, _u32, _u32, _u32]),
     "goofy_b200_encode_host_batch": (_int, [_int, C.POINTER(GoofyB200Image), _u32]),
     "goofy_b200_encode_device": (_int, [_int, _vp, _vp, _u32, _u32, _u32, _vp]),
+    "goofy_b200_encode_rgb24_device": (_int, [_int, _vp, _vp, _vp, _u32, _u32, _u32, _u64, _u64, _u32, _vp]),
     "goofy_b200_encode_relaxed_device": (_int, [_int, _vp, _vp, _u32, _u32, _u32, _vp]),
     "goofy_b200_encode_batch_uniform_device": (_int, [_int, _vp, _vp, _u32, _u32, _u32, _u64, _u64, _u32, _vp]),
     "goofy_b200_encode_dual_device": (_int, [_vp, _vp, _vp, _u32, _u32, _u32, _u64, _u64, _u32, _vp]),

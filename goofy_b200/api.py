@@ -69,6 +69,30 @@ def get_load_path() -> int:
     return int(_lib.load().goofy_b200_get_load_path())
 
 
+HOST_RGB_OFF, HOST_RGB_AUTO, HOST_RGB_ALWAYS = 0, 1, 2
+
+
+def set_host_rgb_staging(mode: int) -> int:
+    """Alpha-stripped staging of the host path (include/goofy_b200.h); returns the previous mode."""
+    return int(_lib.load().goofy_b200_set_host_rgb_staging(mode))
+
+
+def get_host_rgb_staging() -> int:
+    return int(_lib.load().goofy_b200_get_host_rgb_staging())
+
+
+def host_threads() -> int:
+    """Host threads that work on one staging job of the host path, the caller included."""
+    return int(_lib.load().goofy_b200_host_threads())
+
+
+def host_link_stats() -> dict:
+    """Bytes the host path sent host -> device so far, and raw / alpha-stripped strips of large pinned images."""
+    b, r, p = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    _lib.load().goofy_b200_host_link_stats(C.byref(b), C.byref(r), C.byref(p))
+    return {"bytes_uploaded": b.value, "raw_strips": r.value, "packed_strips": p.value}
+
+
 def output_bytes(width: int, height: int) -> int:
     return width * height // 2
 
@@ -183,6 +207,15 @@ def encode_device(codec: int, d_result, d_input, width: int, height: int, stride
     """Asynchronous on `stream` (default: torch's current stream)."""
     return int(_lib.load().goofy_b200_encode_device(codec, _dev_ptr(d_result), _dev_ptr(d_input), width, height,
                                                     stride, _stream_ptr(stream)))
+
+
+def encode_rgb24_device(codec: int, d_result, d_input, width: int, height: int, stride: int, d_result2=None,
+                        input_image_pitch: int = 0, result_image_pitch: int = 0, n_images: int = 1, stream=None) -> int:
+    """Packed RGB8 input (3 bytes per pixel, rows `stride` >= width*3 bytes apart, 4-byte aligned): the same bytes the
+    RGBA entry points produce for the same pixels.  codec may be BOTH (d_result2 = the ETC1s blocks)."""
+    return int(_lib.load().goofy_b200_encode_rgb24_device(
+        codec, _dev_ptr(d_result), _dev_ptr(d_result2), _dev_ptr(d_input), width, height, stride, input_image_pitch,
+        result_image_pitch, n_images, _stream_ptr(stream)))
 
 
 def encode_relaxed_device(codec: int, d_result, d_input, width: int, height: int, stride: int, stream=None) -> int:

@@ -57,6 +57,25 @@ int goofy_b200_set_load_path(int path)
 
 int goofy_b200_get_load_path(void) { return g_loadPath.load(std::memory_order_relaxed); }
 
+int goofy_b200_set_host_rgb_staging(int mode)
+{
+    if (mode < GOOFY_B200_HOST_RGB_OFF || mode > GOOFY_B200_HOST_RGB_ALWAYS) return GOOFY_B200_E_ARGS;
+    const int before = host_rgb_mode();
+    g_hostRgb.store(mode, std::memory_order_relaxed);
+    return before;
+}
+
+int goofy_b200_get_host_rgb_staging(void) { return host_rgb_mode(); }
+
+int goofy_b200_host_threads(void) { return (int)CopyPool::get().threads(); }
+
+void goofy_b200_host_link_stats(uint64_t* bytes_uploaded, uint64_t* raw_strips, uint64_t* packed_strips)
+{
+    if (bytes_uploaded) *bytes_uploaded = g_hostUploaded.load(std::memory_order_relaxed);
+    if (raw_strips) *raw_strips = g_rawStrips.load(std::memory_order_relaxed);
+    if (packed_strips) *packed_strips = g_packedStrips.load(std::memory_order_relaxed);
+}
+
 const char* goofy_b200_error_string(int code)
 {
     switch (code) {
@@ -135,6 +154,14 @@ int goofy_b200_encode_dual_device(void* d_result_dxt1, void* d_result_etc1, cons
 {
     return encode_uniform(gb::kDual, d_result_dxt1, d_result_etc1, d_input, width, height, stride, input_image_pitch,
                           result_image_pitch, n_images, (cudaStream_t)stream);
+}
+
+int goofy_b200_encode_rgb24_device(int codec, void* d_result, void* d_result2, const void* d_input, uint32_t width, uint32_t height,
+                                   uint32_t stride, uint64_t input_image_pitch, uint64_t result_image_pitch, uint32_t n_images,
+                                   void* stream)
+{
+    return encode_rgb24(codec, d_result, d_result2, d_input, width, height, stride, input_image_pitch, result_image_pitch, n_images,
+                        (cudaStream_t)stream);
 }
 
 int goofy_b200_encode_relaxed_device(int codec, void* d_result, const void* d_input, uint32_t width, uint32_t height,

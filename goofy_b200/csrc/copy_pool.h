@@ -6,9 +6,12 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
+
+#include "rgb_pack.h"
 
 namespace {
 
@@ -28,30 +31,16 @@ public:
     // dst/src rows of `rowBytes`, `rows` of them; the calling thread takes a share of the rows too
     void copy2d(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t rows)
     {
-        if (rows * rowBytes < kPoolMinBytes || nWorkers_ == 0) {
-            run(dst, dstPitch, src, srcPitch, rowBytes, 0, rows);
-            return;
-        }
-        std::lock_guard<std::mutex> serial(jobMutex_);  // one copy job at a time
-        dst_ = dst; dstPitch_ = dstPitch; src_ = src; srcPitch_ = srcPitch; rowBytes_ = rowBytes; rows_ = rows;
-        pending_.store((int)nWorkers_, std::memory_order_relaxed);
-        // seq_cst on both sides of the generation_ / sleepers_ handshake (store then load here, store then load in the
-        // worker): at least one side sees the other's write, so a worker cannot go to sleep on a published job
-        generation_.fetch_add(1);   // publishes the job to spinning workers
-        if (sleepers_.load() > 0) {
-            { std::lock_guard<std::mutex> g(m_); }               // a worker between its predicate check and its wait
-            cv_.notify_all();
-        }
-        const size_t parts = nWorkers_ + 1;
-        run(dst, dstPitch, src, srcPitch, rowBytes, rows * (parts - 1) / parts, rows);  // the caller's share: the last slice
-        for (int spin = 0; pending_.load(std::memory_order_acquire) != 0; ++spin) {
-            if (spin < 4096) { cpu_relax(); continue; }
-            std::unique_lock<std::mutex> g(m_);
-            callerWaiting_ = true;
-            done_.wait(g, [this] { return pending_.load(std::memory_order_acquire) == 0; });
-            callerWaiting_ = false;
-        }
+        job2d(dst, dstPitch, src, srcPitch, rowBytes, rows, false);
     }
+    // the same with the alpha byte dropped on the way (rgb_pack.h): src rows of `pixels` RGBA8 pixels -> dst rows of
+    // pixels * 3 bytes
+    void pack2d(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t pixels, size_t rows)
+    {
+        job2d(dst, dstPitch, src, srcPitch, pixels * 4u, rows, true);
+    }
+    // threads that work on one job, the caller included
+    size_t threads() const { return nWorkers_ + 1; }
 
     void copy1d(uint8_t* dst, const uint8_t* src, size_t bytes)
     {
@@ -61,6 +50,33 @@ public:
     }
 
 private:
+    void job2d(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t rows, bool pack)
+    {
+        if (rows * rowBytes < kPoolMinBytes || nWorkers_ == 0) {
+            run(dst, dstPitch, src, srcPitch, rowBytes, 0, rows, pack);
+            return;
+        }
+        std::lock_guard<std::mutex> serial(jobMutex_);  // one copy job at a time
+        dst_ = dst; dstPitch_ = dstPitch; src_ = src; srcPitch_ = srcPitch; rowBytes_ = rowBytes; rows_ = rows; pack_ = pack;
+        pending_.store((int)nWorkers_, std::memory_order_relaxed);
+        // seq_cst on both sides of the generation_ / sleepers_ handshake (store then load here, store then load in the
+        // worker): at least one side sees the other's write, so a worker cannot go to sleep on a published job
+        generation_.fetch_add(1);   // publishes the job to spinning workers
+        if (sleepers_.load() > 0) {
+            { std::lock_guard<std::mutex> g(m_); }               // a worker between its predicate check and its wait
+            cv_.notify_all();
+        }
+        const size_t parts = nWorkers_ + 1;
+        run(dst, dstPitch, src, srcPitch, rowBytes, rows * (parts - 1) / parts, rows, pack);  // the caller's share: the last slice
+        for (int spin = 0; pending_.load(std::memory_order_acquire) != 0; ++spin) {
+            if (spin < 4096) { cpu_relax(); continue; }
+            std::unique_lock<std::mutex> g(m_);
+            callerWaiting_ = true;
+            done_.wait(g, [this] { return pending_.load(std::memory_order_acquire) == 0; });
+            callerWaiting_ = false;
+        }
+    }
+
     static constexpr size_t kPoolMinBytes = 256u << 10;   // smaller copies are done by the caller alone
     static constexpr int kSpinMicros = 50;  // how long an idle worker spins before it sleeps
 
@@ -76,11 +92,24 @@ private:
     {
         unsigned n = std::thread::hardware_concurrency();
         n = n > 16u ? 7u : (n > 2u ? n / 2u - 1u : 0u);  // plus the calling thread
+        // GOOFY_B200_HOST_THREADS = threads per staging job, the caller included (1..64): a launcher that runs one
+        // process per GPU on a shared host divides the cores between them with it
+        if (const char* e = std::getenv("GOOFY_B200_HOST_THREADS")) {
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= 64) n = (unsigned)v - 1u;
+        }
         nWorkers_ = n;
         for (unsigned i = 0; i < n; ++i) std::thread([this, i] { loop(i); }).detach();
     }
-    static void run(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t r0, size_t r1)
+    static void run(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t r0, size_t r1, bool pack)
     {
+        if (pack) {
+            // non-temporal stores: the packed rows are read next by the DMA engine (or by the GPU over the link), never
+            // by this core, and a regular store would first read every destination line into the cache
+            static const bool nt = []() { const char* e = std::getenv("GOOFY_B200_PACK_NT"); return !(e && e[0] == '0'); }();
+            gbpack::pack_rows(dst, dstPitch, src, srcPitch, rowBytes / 4u, r0, r1, nt);
+            return;
+        }
         if (dstPitch == rowBytes && srcPitch == rowBytes) {
             std::memcpy(dst + r0 * rowBytes, src + r0 * rowBytes, (r1 - r0) * rowBytes);
             return;
@@ -102,7 +131,7 @@ private:
             }
             seen = generation_.load(std::memory_order_acquire);
             const size_t parts = nWorkers_ + 1;
-            run(dst_, dstPitch_, src_, srcPitch_, rowBytes_, rows_ * index / parts, rows_ * (index + 1) / parts);
+            run(dst_, dstPitch_, src_, srcPitch_, rowBytes_, rows_ * index / parts, rows_ * (index + 1) / parts, pack_);
             if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
                 std::lock_guard<std::mutex> g(m_);   // the caller may have gone to sleep on done_
                 if (callerWaiting_) done_.notify_one();
@@ -116,6 +145,7 @@ private:
     uint8_t* dst_ = nullptr;
     const uint8_t* src_ = nullptr;
     size_t dstPitch_ = 0, srcPitch_ = 0, rowBytes_ = 0, rows_ = 0;
+    bool pack_ = false;
     std::atomic<int> pending_{0};
     std::atomic<int> sleepers_{0};
     std::atomic<uint64_t> generation_{0};

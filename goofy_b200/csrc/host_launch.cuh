@@ -470,6 +470,81 @@ int encode_floatref(int codec, void* dst, const void* src, uint32_t width, uint3
     return GOOFY_B200_OK;
 }
 
+// Packed RGB8 input (encode_kernels.cuh: encode_rgb24_kernel).  codec: DXT1, ETC1, BOTH (dst2 = the ETC1s blocks) or a
+// float-reference flavour.  Rows and the base pointer only need 4-byte alignment (a tightly packed image with
+// width % 4 == 0 qualifies); the shape rules are the codec's own.
+int encode_rgb24(int codec, void* dst, void* dst2, const void* src, uint32_t width, uint32_t height, uint32_t stride, uint64_t srcPitch,
+                 uint64_t dstPitch, uint32_t nImages, cudaStream_t stream)
+{
+    const bool both = codec == GOOFY_B200_BOTH;
+    if (!both && !is_codec(codec)) return GOOFY_B200_E_CODEC;
+    if (width % (is_floatref(codec) ? 4u : 16u) != 0u) return GOOFY_B200_E_WIDTH;
+    if (height % 4u != 0u) return GOOFY_B200_E_HEIGHT;
+    if (width == 0u || height == 0u || nImages == 0u) return GOOFY_B200_OK;
+    if ((uint64_t)stride < (uint64_t)width * 3u) return GOOFY_B200_E_STRIDE;
+    if (!src || !dst || (both && !dst2)) return GOOFY_B200_E_NULL;
+    if (((uintptr_t)src & 3u) != 0u || (stride & 3u) != 0u || ((uintptr_t)dst & 7u) != 0u || (both && ((uintptr_t)dst2 & 7u) != 0u))
+        return GOOFY_B200_E_ALIGN;
+    if (nImages > 1u) {
+        if ((srcPitch & 3u) != 0u || (dstPitch & 7u) != 0u) return GOOFY_B200_E_ALIGN;
+        if (srcPitch < (uint64_t)(height - 1u) * stride + (uint64_t)width * 3u || dstPitch < (uint64_t)width * height / 2u) return GOOFY_B200_E_ARGS;
+    }
+    int dev = -1;
+    int rc = ensure_device_ready(&dev);
+    if (rc != GOOFY_B200_OK) return rc;
+    const int sms = sm_count(dev);
+    if (sms <= 0) return GOOFY_B200_E_DEVICE;
+
+    gb::EncodeParams P = {};
+    P.src = (const uint8_t*)src;
+    P.dst = (uint8_t*)dst;
+    P.dst2 = (uint8_t*)dst2;
+    P.bw = width / 4u;
+    P.bh = height / 4u;
+    P.stride = stride;
+    P.srcPitch = srcPitch;
+    P.dstPitch = dstPitch;
+    uint32_t tx = 32u;
+    while (tx < 256u && tx < P.bw) tx <<= 1;
+    const uint32_t ty = 256u / tx;
+    const dim3 block(tx, ty, 1);
+    const uint32_t gx = (P.bw + tx - 1u) / tx, rowGroups = (P.bh + ty - 1u) / ty;
+    // a few block rows per CTA, never fewer CTAs than are resident at once (launch_rows has the measurements)
+    const int mode = both ? gb::kDual : (codec == GOOFY_B200_ETC1 || codec == GOOFY_B200_ETC1_FLOATREF) ? gb::kEtc1 : gb::kDxt1;
+    const uint32_t resident = (uint32_t)sms * (uint32_t)gb::rgb24_ctas_per_sm(mode);
+    static const uint32_t rowsEnv = (uint32_t)env_int("GOOFY_B200_RGB24_ROWS_PER_CTA", 1, 1 << 20, 0);
+    static const bool rgb24Coop = env_int("GOOFY_B200_RGB24_COOP", 0, 1, 1) != 0;   // 0: 32-bit loads everywhere (A/B runs)
+    uint32_t gy = (rowGroups + (rowsEnv ? rowsEnv : 4u) - 1u) / (rowsEnv ? rowsEnv : 4u);
+    const uint32_t perImage = (resident + nImages - 1u) / nImages;
+    if (gy < perImage / gx) gy = perImage / gx;
+    if (gy == 0u) gy = 1u;
+    if (gy > rowGroups) gy = rowGroups;
+    if (gy > 65535u) gy = 65535u;
+    for (uint32_t img0 = 0; img0 < nImages; img0 += 65535u) {
+        const uint32_t nz = nImages - img0 < 65535u ? nImages - img0 : 65535u;
+        gb::EncodeParams Q = P;
+        Q.src += (uint64_t)img0 * srcPitch;
+        Q.dst += (uint64_t)img0 * dstPitch;
+        if (Q.dst2) Q.dst2 += (uint64_t)img0 * dstPitch;
+        const dim3 grid(gx, gy, nz);
+        // warp-cooperative 128-bit loads when every pixel row starts on a 16-byte boundary; else 32-bit loads per thread
+        const bool coop = (((uintptr_t)Q.src | stride | (nz > 1u ? srcPitch : 0u)) & 15u) == 0u && width % 16u == 0u && rgb24Coop;
+#define GB_RGB24(MODE, FLAV, NAME)                                                                                              \
+    (coop ? launch_encode(gb::encode_rgb24_kernel<MODE, FLAV, true>, grid, block, stream, Q, "encode_rgb24_kernel<" NAME ">")     \
+          : launch_encode(gb::encode_rgb24_kernel<MODE, FLAV, false>, grid, block, stream, Q, "encode_rgb24_kernel[32-bit loads]<" NAME ">"))
+        switch (codec) {
+            case GOOFY_B200_DXT1: rc = GB_RGB24(gb::kDxt1, 0, "dxt1"); break;
+            case GOOFY_B200_ETC1: rc = GB_RGB24(gb::kEtc1, 0, "etc1s"); break;
+            case GOOFY_B200_BOTH: rc = GB_RGB24(gb::kDual, 0, "dxt1+etc1s"); break;
+            case GOOFY_B200_DXT1_FLOATREF: rc = GB_RGB24(gb::kDxt1, 1, "dxt1, float reference"); break;
+            default: rc = GB_RGB24(gb::kEtc1, 1, "etc1s, float reference"); break;
+        }
+#undef GB_RGB24
+        if (rc != GOOFY_B200_OK) return rc;
+    }
+    return GOOFY_B200_OK;
+}
+
 // Device-resident dispatch by codec selector (SSE2-exact or float-reference-exact flavour).
 int encode_any(int codec, void* dst, const void* src, uint32_t width, uint32_t height, uint32_t stride, uint64_t srcPitch,
                uint64_t dstPitch, uint32_t nImages, cudaStream_t stream)

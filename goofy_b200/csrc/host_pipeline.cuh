@@ -26,6 +26,23 @@ bool is_pageable(const void* p)
     return pageable;
 }
 
+// Alpha-stripped staging (rgb_pack.h): 0 = never, 1 = AUTO, 2 = every strip of a pinned image too (experiments).
+// AUTO: pageable input is staged as packed RGB (the staging copy has to be made anyway; it then writes, and the link
+// then carries, 3 bytes per pixel instead of 4); large pinned input goes through the hybrid scheduler (run_hybrid).
+std::atomic<int> g_hostRgb{-1};
+int host_rgb_mode()
+{
+    int m = g_hostRgb.load(std::memory_order_relaxed);
+    if (m < 0) {
+        m = env_int("GOOFY_B200_HOST_RGB", 0, 2, 1);
+        g_hostRgb.store(m, std::memory_order_relaxed);
+    }
+    return m;
+}
+// bytes that crossed the link host -> device through the host path (copy engine or zero-copy kernel reads), and
+// strips of pinned images sent as they were / alpha-stripped first: what a benchmark reports instead of assuming
+std::atomic<uint64_t> g_hostUploaded{0}, g_rawStrips{0}, g_packedStrips{0};
+
 constexpr size_t kStagePieceBytes = 768u << 10;   // zero-copy path: smallest piece of a strip staged and encoded on its own
 constexpr size_t kCopyPieceBytes = 2u << 20;      // copying path: smallest piece of a strip staged and sent on its own
 
@@ -53,6 +70,15 @@ struct HostTrace {
 thread_local HostTrace t_trace;
 thread_local int t_hostCalls = 0;
 
+inline void cpu_pause()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+}
+
 // One host image of a host-pointer call, validated and cut into strips.
 struct HostJob {
     const uint8_t* input = nullptr;
@@ -62,6 +88,8 @@ struct HostJob {
     uint32_t width = 0, stride = 0, blockRows = 0, stripRows = 0;
     size_t rowBytes = 0, outRowBytes = 0;
     bool stageIn = false, stageOut = false;
+    bool packIn = false;      // pageable input staged as packed RGB (3 bytes per pixel) and encoded by the rgb24 kernels
+    size_t stagedRowBytes = 0;   // bytes per pixel row as staged / uploaded: rowBytes, or width * 3 when packIn
 };
 
 // Strips of whole block rows: about eight per image so that staging, H2D, kernel and D2H of neighbouring strips
@@ -106,6 +134,134 @@ int make_host_job(int codec, void* result, const void* input, uint32_t width, ui
     // Pinned buffers are DMA'd in place; pageable ones go through the pinned staging strips.
     job.stageIn = is_pageable(input);
     job.stageOut = is_pageable(result);
+    job.packIn = job.stageIn && host_rgb_mode() != 0;
+    job.stagedRowBytes = job.packIn ? (size_t)width * 3u : job.rowBytes;
+    return GOOFY_B200_OK;
+}
+
+// Large PINNED input: the hybrid scheduler.  The call is bound by the link (4 of the 4.5 bytes per pixel that cross it
+// are input, a quarter of them alpha bytes nobody reads), and the host's cores idle while it runs.  So strips are
+// claimed from both ends of the image: from the FRONT they are DMA'd as they are; from the BACK the calling thread and
+// the copy pool first drop the alpha byte (CopyPool::pack2d, into a small ring of pinned strips) and 3 bytes per pixel
+// cross instead of 4, encoded by the rgb24 kernels.  The two kinds meet wherever the host's packing rate puts them: the
+// caller keeps enough raw uploads queued to cover the time one pack takes (measured, a running mean) and packs only
+// while that much is queued, so a host with no cores to spare degrades to the plain DMA pipeline and a host with
+// plenty sends nearly everything packed.  With packing rate P and link rate L (input bytes per second) the share of
+// packed strips settles at x = 1 / (L / P + 1/4) (capped at 1) and the call takes x / P: 0.8 of the plain time at
+// P = L, 0.75 from P = 4/3 L on.
+int run_hybrid(int codec, const HostJob& J, ThreadResources& R, int dev)
+{
+    static const size_t stripTarget = (size_t)env_int("GOOFY_B200_HYBRID_STRIP_KB", 256, 16384, 4096) << 10;
+    static const double linkGBs = (double)env_int("GOOFY_B200_HYBRID_LINK_GBS", 1, 1000, 50);   // only sizes the queue
+    uint32_t stripRows = (uint32_t)(stripTarget / (J.rowBytes * 4u));
+    if (stripRows == 0u) stripRows = 1u;
+    const uint32_t nStrips = (J.blockRows + stripRows - 1u) / stripRows;
+    const size_t stripIn = (size_t)stripRows * 4u * J.rowBytes, packedRow = (size_t)J.width * 3u;
+    const size_t stripPacked = (size_t)stripRows * 4u * packedRow;
+    const size_t half = (size_t)stripRows * J.outRowBytes;
+    int rc = R.pipe.prepare(dev, stripIn, half * (J.result2 ? 2u : 1u));
+    if (rc != GOOFY_B200_OK) return rc;
+    rc = R.pipe.ensure_events();
+    if (rc != GOOFY_B200_OK) return rc;
+    rc = R.stage.ensure_pack(stripPacked);
+    if (rc != GOOFY_B200_OK) return rc;
+
+    struct Flight { bool busy = false; size_t bytes = 0; int packSlot = -1; } flight[kFlights];
+    bool packBusy[kPackSlots] = {};
+    size_t queuedBytes = 0;
+    int nFlights = 0;
+    auto poll = [&]() -> int {   // retire uploads that have finished
+        for (int i = 0; i < kFlights; ++i) {
+            if (!flight[i].busy) continue;
+            const cudaError_t e = cudaEventQuery(R.pipe.uploaded[i]);
+            if (e == cudaErrorNotReady) continue;
+            if (e != cudaSuccess) return cuda_rc(e);
+            flight[i].busy = false;
+            queuedBytes -= flight[i].bytes;
+            --nFlights;
+            if (flight[i].packSlot >= 0) packBusy[flight[i].packSlot] = false;
+        }
+        return GOOFY_B200_OK;
+    };
+    auto fail = [&](int code) -> int {
+        for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(R.pipe.stream[i]);
+        cudaGetLastError();
+        return code;
+    };
+    uint32_t issued = 0;
+    // upload (raw, or from pack slot `packSlot`) -> kernel -> download of strip k, on the next stream round-robin
+    auto issue = [&](uint32_t k, int packSlot) -> int {
+        const int slot = (int)(issued++ % (uint32_t)kSlots);
+        cudaStream_t s = R.pipe.stream[slot];
+        const uint32_t r0 = k * stripRows, rows = J.blockRows - r0 < stripRows ? J.blockRows - r0 : stripRows;
+        int f = 0;
+        while (flight[f].busy) ++f;   // the caller made sure one is free
+        const size_t bytes = (size_t)rows * 4u * (packSlot >= 0 ? packedRow : J.rowBytes);
+        if (packSlot >= 0)
+            GB_CUDA(cudaMemcpyAsync(R.pipe.dIn[slot], R.stage.pack[packSlot], bytes, cudaMemcpyHostToDevice, s));
+        else
+            GB_CUDA(cudaMemcpy2DAsync(R.pipe.dIn[slot], J.rowBytes, J.input + (size_t)r0 * 4u * J.stride, J.stride, J.rowBytes, (size_t)rows * 4u,
+                                      cudaMemcpyHostToDevice, s));
+        GB_CUDA(cudaEventRecord(R.pipe.uploaded[f], s));
+        flight[f].busy = true;
+        flight[f].bytes = bytes;
+        flight[f].packSlot = packSlot;
+        queuedBytes += bytes;
+        ++nFlights;
+        g_hostUploaded.fetch_add(bytes, std::memory_order_relaxed);
+        (packSlot >= 0 ? g_packedStrips : g_rawStrips).fetch_add(1, std::memory_order_relaxed);
+        uint8_t* dOut = (uint8_t*)R.pipe.dOut[slot];
+        int r;
+        if (packSlot >= 0)
+            r = encode_rgb24(J.result2 ? GOOFY_B200_BOTH : codec, dOut, dOut + half, R.pipe.dIn[slot], J.width, rows * 4u, (uint32_t)packedRow, 0, 0, 1, s);
+        else
+            r = J.result2 ? encode_uniform(gb::kDual, dOut, dOut + half, R.pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s)
+                          : encode_any(codec, dOut, R.pipe.dIn[slot], J.width, rows * 4u, (uint32_t)J.rowBytes, 0, 0, 1, s);
+        if (r != GOOFY_B200_OK) return r;
+        GB_CUDA(cudaMemcpyAsync(J.result + (size_t)r0 * J.outRowBytes, dOut, (size_t)rows * J.outRowBytes, cudaMemcpyDeviceToHost, s));
+        if (J.result2)
+            GB_CUDA(cudaMemcpyAsync(J.result2 + (size_t)r0 * J.outRowBytes, dOut + half, (size_t)rows * J.outRowBytes, cudaMemcpyDeviceToHost, s));
+        return GOOFY_B200_OK;
+    };
+
+    const bool packAll = host_rgb_mode() == 2;
+    // seconds one pack of a full strip takes: a running mean, seeded per calling thread by its previous call
+    thread_local double packSeconds = 0.0;
+    if (packSeconds == 0.0) packSeconds = (double)stripIn / 30e9;
+    uint32_t front = 0, back = nStrips;
+    while (front < back) {
+        rc = poll();
+        if (rc != GOOFY_B200_OK) return fail(rc);
+        // queued upload time that covers one pack, with a margin; never less than two raw strips
+        double cover = packSeconds * 1.25 * linkGBs * 1e9;
+        if (cover < 2.0 * (double)stripIn) cover = 2.0 * (double)stripIn;
+        if (!packAll && (double)queuedBytes < cover && nFlights < kFlights) {
+            rc = issue(front++, -1);
+            if (rc != GOOFY_B200_OK) return fail(rc);
+            continue;
+        }
+        int ps = 0;
+        while (ps < kPackSlots && packBusy[ps]) ++ps;
+        if (ps < kPackSlots && nFlights < kFlights) {
+            const uint32_t k = --back;
+            const uint32_t r0 = k * stripRows, rows = J.blockRows - r0 < stripRows ? J.blockRows - r0 : stripRows;
+            const auto t0 = std::chrono::steady_clock::now();
+            CopyPool::get().pack2d((uint8_t*)R.stage.pack[ps], packedRow, J.input + (size_t)r0 * 4u * J.stride, J.stride, J.width, (size_t)rows * 4u);
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * (double)stripRows / (double)rows;
+            packSeconds = 0.75 * packSeconds + 0.25 * dt;
+            packBusy[ps] = true;
+            rc = poll();
+            if (rc != GOOFY_B200_OK) return fail(rc);
+            rc = issue(k, ps);
+            if (rc != GOOFY_B200_OK) return fail(rc);
+            continue;
+        }
+        cpu_pause();
+    }
+    for (int i = 0; i < kSlots; ++i) {
+        const cudaError_t e = cudaStreamSynchronize(R.pipe.stream[i]);
+        if (e != cudaSuccess) return fail(cuda_rc(e));
+    }
     return GOOFY_B200_OK;
 }
 
@@ -119,7 +275,7 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         const HostJob& J = jobs[j];
         if (J.blockRows == 0u) continue;
         // dual-output jobs keep their second result in the upper half of the slot's output scratch / staging strip
-        const size_t in = (size_t)J.stripRows * 4u * J.rowBytes, out = (size_t)J.stripRows * J.outRowBytes * (J.result2 ? 2u : 1u);
+        const size_t in = (size_t)J.stripRows * 4u * J.stagedRowBytes, out = (size_t)J.stripRows * J.outRowBytes * (J.result2 ? 2u : 1u);
         needIn = in > needIn ? in : needIn;
         needOut = out > needOut ? out : needOut;
         if (J.stageIn && in > needStageIn) needStageIn = in;
@@ -155,8 +311,15 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
     };
     // The encode launch of one strip (or one piece of it): both codecs when the job has a second result.
     auto launch = [&](const HostJob& J, uint8_t* out, uint8_t* out2, const uint8_t* in, uint32_t pixelRows, uint32_t stride, cudaStream_t s) -> int {
+        if (J.packIn) return encode_rgb24(J.result2 ? GOOFY_B200_BOTH : codec, out, out2, in, J.width, pixelRows, stride, 0, 0, 1, s);
         return J.result2 ? encode_uniform(gb::kDual, out, out2, in, J.width, pixelRows, stride, 0, 0, 1, s)
                          : encode_any(codec, out, in, J.width, pixelRows, stride, 0, 0, 1, s);
+    };
+    // stage rows [y0, y1) of a strip into pinned memory: a plain copy, or with the alpha byte dropped on the way
+    auto stage_rows = [&](const HostJob& J, uint8_t* stage, const uint8_t* src, size_t rows) {
+        if (J.packIn) CopyPool::get().pack2d(stage, J.stagedRowBytes, src, J.stride, J.width, rows);
+        else CopyPool::get().copy2d(stage, J.rowBytes, src, J.stride, J.rowBytes, rows);
+        g_hostUploaded.fetch_add(rows * J.stagedRowBytes, std::memory_order_relaxed);
     };
     // Small strips (a test-image-sized texture is ONE strip of 1.5 MiB) skip the copy engine altogether: the kernel reads
     // the pinned input -- the caller's buffer, or the staging strip -- straight over PCIe and writes its blocks straight
@@ -193,6 +356,7 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         taken = true;
         if (!J.stageIn) {
             const int r = launch(J, outDev, out2Dev, inDev, rows * 4u, J.stride, s);
+            g_hostUploaded.fetch_add((size_t)rows * 4u * J.rowBytes, std::memory_order_relaxed);
             t_trace.mark("zero-copy kernel launched (pinned input)");
             if (r != GOOFY_B200_OK) return r;
         } else {
@@ -201,11 +365,11 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
             if (pieces > rows) pieces = rows;
             for (size_t k = 0; k < pieces; ++k) {
                 const size_t b0 = (size_t)rows * k / pieces, b1 = (size_t)rows * (k + 1u) / pieces;   // block rows of this piece
-                uint8_t* stage = (uint8_t*)R.stage.in[slot] + b0 * 4u * J.rowBytes;
-                CopyPool::get().copy2d(stage, J.rowBytes, src + b0 * 4u * J.stride, J.stride, J.rowBytes, (b1 - b0) * 4u);
-                t_trace.mark("piece staged into pinned memory");
+                uint8_t* stage = (uint8_t*)R.stage.in[slot] + b0 * 4u * J.stagedRowBytes;
+                stage_rows(J, stage, src + b0 * 4u * J.stride, (b1 - b0) * 4u);
+                t_trace.mark(J.packIn ? "piece staged into pinned memory, alpha dropped" : "piece staged into pinned memory");
                 const int r = launch(J, outDev + b0 * J.outRowBytes, out2Dev ? out2Dev + b0 * J.outRowBytes : nullptr,
-                                     inDev + b0 * 4u * J.rowBytes, (uint32_t)(b1 - b0) * 4u, (uint32_t)J.rowBytes, s);
+                                     inDev + b0 * 4u * J.stagedRowBytes, (uint32_t)(b1 - b0) * 4u, (uint32_t)J.stagedRowBytes, s);
                 t_trace.mark("zero-copy kernel launched on the piece");
                 if (r != GOOFY_B200_OK) return r;
             }
@@ -244,19 +408,20 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
             pieces = pieces < 1u ? 1u : (pieces > 4u ? 4u : pieces);
             for (size_t k = 0; k < pieces; ++k) {
                 const size_t y0 = pixelRows * k / pieces, y1 = pixelRows * (k + 1u) / pieces;
-                uint8_t* stage = (uint8_t*)R.stage.in[slot] + y0 * J.rowBytes;
-                CopyPool::get().copy2d(stage, J.rowBytes, src + y0 * J.stride, J.stride, J.rowBytes, y1 - y0);
+                uint8_t* stage = (uint8_t*)R.stage.in[slot] + y0 * J.stagedRowBytes;
+                stage_rows(J, stage, src + y0 * J.stride, y1 - y0);
                 t_trace.mark("piece staged into pinned memory");
-                GB_CUDA(cudaMemcpyAsync((uint8_t*)R.pipe.dIn[slot] + y0 * J.rowBytes, stage, (y1 - y0) * J.rowBytes, cudaMemcpyHostToDevice, s));
+                GB_CUDA(cudaMemcpyAsync((uint8_t*)R.pipe.dIn[slot] + y0 * J.stagedRowBytes, stage, (y1 - y0) * J.stagedRowBytes, cudaMemcpyHostToDevice, s));
                 t_trace.mark("piece H2D issued");
             }
         } else {
             GB_CUDA(cudaMemcpy2DAsync(R.pipe.dIn[slot], J.rowBytes, src, J.stride, J.rowBytes, (size_t)rows * 4u, cudaMemcpyHostToDevice, s));
+            g_hostUploaded.fetch_add((size_t)rows * 4u * J.rowBytes, std::memory_order_relaxed);
             t_trace.mark("H2D issued (pinned input)");
         }
         const size_t half = (size_t)J.stripRows * J.outRowBytes;   // where a dual-output job keeps its ETC1s blocks
         uint8_t* dOut = (uint8_t*)R.pipe.dOut[slot];
-        const int r = launch(J, dOut, dOut + half, (const uint8_t*)R.pipe.dIn[slot], rows * 4u, (uint32_t)J.rowBytes, s);
+        const int r = launch(J, dOut, dOut + half, (const uint8_t*)R.pipe.dIn[slot], rows * 4u, (uint32_t)J.stagedRowBytes, s);
         if (r != GOOFY_B200_OK) return r;
         t_trace.mark("kernel launched");
         GB_CUDA(cudaMemcpyAsync(J.stageOut ? R.stage.out[slot] : (void*)(J.result + (size_t)r0 * J.outRowBytes), dOut,
@@ -280,6 +445,18 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
     int slot = 0;
     for (uint32_t j = 0; j < nJobs; ++j) {
         const HostJob& J = jobs[j];
+        // large pinned images (the ones that would go through the copy engine strip by strip): the hybrid scheduler
+        if (!J.stageIn && !J.stageOut && !J.stageOut2 && J.blockRows != 0u && host_rgb_mode() != 0 &&
+            (size_t)J.blockRows * 4u * J.rowBytes > zeroCopyMax) {
+            for (int i = 0; i < kSlots; ++i, slot = (slot + 1) % kSlots) {
+                rc = retire(slot);
+                if (rc != GOOFY_B200_OK) return fail(rc);
+            }
+            rc = run_hybrid(codec, J, R, dev);
+            if (rc != GOOFY_B200_OK) return rc;
+            t_trace.mark("hybrid pinned image done");
+            continue;
+        }
         for (uint32_t r0 = 0; r0 < J.blockRows; r0 += J.stripRows, slot = (slot + 1) % kSlots) {
             const uint32_t rows = J.blockRows - r0 < J.stripRows ? J.blockRows - r0 : J.stripRows;
             rc = issue(slot, J, r0, rows);

@@ -18,6 +18,8 @@ namespace {
 // Device scratch only ever grows.
 constexpr int kSlots = 3;
 constexpr size_t kStripBytes = 16u << 20;
+constexpr int kFlights = 24;     // hybrid pinned path: uploads that may be queued on the link at once
+constexpr int kPackSlots = 4;    // ... and pinned strips that hold alpha-stripped pixels on their way to the device
 
 struct HostPipe {
     int device = -1;
@@ -26,6 +28,7 @@ struct HostPipe {
     void* dOut[kSlots] = {};
     size_t capIn = 0, capOut = 0;
     bool ready = false;
+    cudaEvent_t uploaded[kFlights] = {};   // created on first use by the hybrid pinned path
 
     int prepare(int dev, size_t needIn, size_t needOut)
     {
@@ -55,6 +58,12 @@ struct HostPipe {
         }
         return GOOFY_B200_OK;
     }
+    int ensure_events()
+    {
+        for (int i = 0; i < kFlights; ++i)
+            if (!uploaded[i]) GB_CUDA(cudaEventCreateWithFlags(&uploaded[i], cudaEventDisableTiming));
+        return GOOFY_B200_OK;
+    }
     void release()   // the set moves to another device: its streams and strips belong to the old one
     {
         for (int i = 0; i < kSlots; ++i) {
@@ -63,6 +72,10 @@ struct HostPipe {
             if (stream[i]) cudaStreamDestroy(stream[i]);
             dIn[i] = dOut[i] = nullptr;
             stream[i] = nullptr;
+        }
+        for (int i = 0; i < kFlights; ++i) {
+            if (uploaded[i]) cudaEventDestroy(uploaded[i]);
+            uploaded[i] = nullptr;
         }
         cudaGetLastError();
         capIn = capOut = 0;
@@ -74,7 +87,21 @@ struct HostPipe {
 struct HostStage {
     void* in[kSlots] = {};
     void* out[kSlots] = {};
-    size_t capIn = 0, capOut = 0;
+    void* pack[kPackSlots] = {};   // hybrid pinned path: alpha-stripped strips
+    size_t capIn = 0, capOut = 0, capPack = 0;
+    int ensure_pack(size_t need)
+    {
+        if (need > capPack) {
+            capPack = 0;
+            for (int i = 0; i < kPackSlots; ++i) {
+                if (pack[i]) cudaFreeHost(pack[i]);
+                pack[i] = nullptr;
+                GB_CUDA(cudaHostAlloc(&pack[i], need, cudaHostAllocDefault));
+            }
+            capPack = need;
+        }
+        return GOOFY_B200_OK;
+    }
     int ensure(size_t needIn, size_t needOut)
     {
         if (needIn > capIn) {

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GOOFY_B200_ABI_VERSION 2   /* 2: GoofyB200Image gained dst2, GOOFY_B200_BOTH */
+#define GOOFY_B200_ABI_VERSION 3   /* 2: GoofyB200Image gained dst2, GOOFY_B200_BOTH; 3: packed-RGB input, host-path knobs */
 
 /* codec selectors */
 #define GOOFY_B200_DXT1 0
@@ -102,6 +102,27 @@ uint64_t goofy_b200_host_scratch_sets(void);
 int goofy_b200_set_load_path(int path);
 int goofy_b200_get_load_path(void);
 
+/* Host path: drop the alpha byte while staging (the encoders ignore it; 4 of the 4.5 bytes per pixel that cross PCIe
+ * are input).  Process-wide; set returns the previous setting (or GOOFY_B200_E_ARGS).
+ *   OFF     every pixel crosses the link as RGBA
+ *   AUTO    (default) pageable input is staged as packed RGB -- the staging copy is made anyway; large pinned input is
+ *           split between plain DMA and alpha-stripped strips according to how fast the host's cores pack (a host with
+ *           none to spare degrades to plain DMA)
+ *   ALWAYS  every strip of a large pinned image is alpha-stripped first (experiments)
+ * The bytes produced are identical in every mode.  Environment: GOOFY_B200_HOST_RGB=0|1|2 (initial mode),
+ * GOOFY_B200_HOST_THREADS=n (host threads per staging job, the caller included; default min(8, cores / 2)). */
+#define GOOFY_B200_HOST_RGB_OFF 0
+#define GOOFY_B200_HOST_RGB_AUTO 1
+#define GOOFY_B200_HOST_RGB_ALWAYS 2
+int goofy_b200_set_host_rgb_staging(int mode);
+int goofy_b200_get_host_rgb_staging(void);
+/* Host threads that work on one staging job (copy or alpha strip), the calling thread included. */
+int goofy_b200_host_threads(void);
+/* What the host path sent over the link so far in this process (all threads): bytes host -> device (copy engine and
+ * zero-copy kernel reads), and strips of large pinned images sent as they were / alpha-stripped first.  Any pointer
+ * may be NULL. */
+void goofy_b200_host_link_stats(uint64_t* bytes_uploaded, uint64_t* raw_strips, uint64_t* packed_strips);
+
 /* ---- drop-in host-pointer API: same arguments, order and return codes as the reference ---- */
 int goofy_b200_compress_dxt1(unsigned char* result, const unsigned char* input, unsigned int width,
                              unsigned int height, unsigned int stride);
@@ -140,6 +161,17 @@ int goofy_b200_encode_device(int codec, void* d_result, const void* d_input, uin
  * Meant for odd-sized mip levels; it uses scalar loads and is not the bandwidth-optimal path. */
 int goofy_b200_encode_relaxed_device(int codec, void* d_result, const void* d_input, uint32_t width, uint32_t height,
                                      uint32_t stride, void* stream);
+
+/* Packed RGB8 input: 3 bytes per pixel, NO alpha byte (the encoders ignore alpha, GoofyTC/goofy_tc.h:297), rows
+ * `stride` >= width*3 bytes apart; d_input, stride and input_image_pitch only need 4-byte alignment.  The bytes
+ * produced are those the RGBA entry points produce for the same pixels with any alpha.  3.5 instead of 4.5 bytes of
+ * memory traffic per pixel, for callers whose pixels are RGB to begin with (decoded PNG / JPEG) and for the host path,
+ * which drops the alpha byte while staging (goofy_b200_set_host_rgb_staging).  codec: GOOFY_B200_DXT1, _ETC1, _BOTH
+ * (d_result2 = the ETC1s blocks, ignored otherwise) or a float-reference flavour.  n_images at fixed pitches
+ * (pitches ignored for n_images == 1). */
+int goofy_b200_encode_rgb24_device(int codec, void* d_result, void* d_result2, const void* d_input, uint32_t width,
+                                   uint32_t height, uint32_t stride, uint64_t input_image_pitch,
+                                   uint64_t result_image_pitch, uint32_t n_images, void* stream);
 
 /* n images of one shape laid out at fixed pitches (bytes) from d_input / d_result. */
 int goofy_b200_encode_batch_uniform_device(int codec, void* d_result, const void* d_input, uint32_t width,

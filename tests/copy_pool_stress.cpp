@@ -25,6 +25,21 @@ int main(int argc, char** argv)
             }
             ++checks;
         }
+        if (it % 3 == 0) {   // the alpha-stripping job (pack2d) through the same handshake: 1024 pixels per row
+            const size_t pixels = rowBytes / 4u;
+            std::memset(dst.data(), 0, rows * pixels * 3u);
+            CopyPool::get().pack2d(dst.data(), pixels * 3u, src.data(), pitch, pixels, rows);
+            for (size_t r = 0; r < rows; r += 13) {
+                const uint8_t* d = dst.data() + r * pixels * 3u;
+                const uint8_t* q = src.data() + r * pitch;
+                for (size_t x = 0; x < pixels; ++x)
+                    if (d[3 * x] != q[4 * x] || d[3 * x + 1] != q[4 * x + 1] || d[3 * x + 2] != q[4 * x + 2]) {
+                        std::printf("PACK MISMATCH job %d row %zu pixel %zu\n", it, r, x);
+                        return 1;
+                    }
+                ++checks;
+            }
+        }
         if (it % 5 == 0) std::this_thread::sleep_for(std::chrono::microseconds(it % 300));  // lets the workers fall asleep
         if (it % 7 == 0) CopyPool::get().copy1d(dst.data(), src.data(), 300000 + (size_t)it);
     }

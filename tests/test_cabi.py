@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert lib.goofy_b200_abi_version() == 2
+    assert lib.goofy_b200_abi_version() == 3
 
 
 def test_cpp_header_keeps_reference_signatures():

@@ -1,0 +1,227 @@
+"""Packed-RGB input (goofy_b200_encode_rgb24_device) and the alpha-stripping host path built on it: the bytes must be
+those the RGBA path produces, i.e. those of the oracle / the unmodified reference on the same pixels with any alpha
+(the encoders ignore alpha, GoofyTC/goofy_tc.h:297)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import goofy_b200 as gb  # noqa: E402
+from oracle.oracle import DXT1, ETC1, aligned_copy, image_names, load_test_image, splitmix_rgba, synth_family  # noqa: E402
+
+CODECS = [DXT1, ETC1]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rgb_of(img, w, h, stride=None, pad=0xCD):
+    """RGBA (h, w, 4) -> packed RGB rows `stride` bytes apart (default tight), padding filled with `pad`."""
+    stride = w * 3 if stride is None else stride
+    out = np.full((h, stride), pad, dtype=np.uint8)
+    out[:, : w * 3] = np.ascontiguousarray(img).reshape(h, w, 4)[..., :3].reshape(h, w * 3)
+    return out
+
+
+def rgb24_device(codec, img, w, h, stride=None, base_offset=0):
+    stride = w * 3 if stride is None else stride
+    rows = rgb_of(img, w, h, stride).reshape(-1)
+    d_all = torch.zeros(rows.size + base_offset + 64, dtype=torch.uint8, device="cuda")
+    d_all[base_offset: base_offset + rows.size] = dev(rows)
+    d_src = d_all[base_offset:]
+    d_dst = torch.zeros(max(w * h // 2, 8), dtype=torch.uint8, device="cuda")
+    d_dst2 = torch.zeros(max(w * h // 2, 8), dtype=torch.uint8, device="cuda")
+    rc = gb.encode_rgb24_device(codec, d_dst, d_src, w, h, stride, d_result2=d_dst2 if codec == gb.BOTH else None)
+    torch.cuda.synchronize()
+    return rc, d_dst.cpu().numpy()[: w * h // 2], d_dst2.cpu().numpy()[: w * h // 2]
+
+
+@pytest.mark.parametrize("codec", CODECS)
+@pytest.mark.parametrize("family", [0, 1, 2, 3])
+def test_rgb24_synthetic_families_vs_oracle(codec, family, oracle):
+    for (w, h, seed) in ((256, 256, 1), (1024, 512, 77), (2064, 36, 5)):
+        img = synth_family(family, w, h, seed=seed)
+        rc, got, _ = rgb24_device(codec, img, w, h)
+        assert rc == 0 and "rgb24" in gb.last_launch_kernel() and "32-bit" not in gb.last_launch_kernel()
+        assert np.array_equal(got, oracle.compress(codec, img, w, h)[1]), (family, w, h)
+
+
+@pytest.mark.parametrize("shape", [(16, 4), (16, 8), (32, 4), (48, 12), (112, 20), (144, 4), (528, 36), (1040, 8), (4112, 4), (8192, 16)])
+def test_rgb24_ragged_shapes_all_outputs(shape, oracle):
+    """Every width class: warps with fewer than 32 live blocks, CTAs stacking several block rows, both codecs from one read."""
+    w, h = shape
+    img = splitmix_rgba(w * h, seed=w * 31 + h)
+    want = {c: oracle.compress(c, img, w, h)[1] for c in CODECS}
+    for codec in CODECS:
+        rc, got, _ = rgb24_device(codec, img, w, h)
+        assert rc == 0 and np.array_equal(got, want[codec]), (codec, shape)
+    rc, got, got2 = rgb24_device(gb.BOTH, img, w, h)
+    assert rc == 0 and np.array_equal(got, want[DXT1]) and np.array_equal(got2, want[ETC1]), shape
+
+
+@pytest.mark.parametrize("codec", CODECS + [gb.BOTH])
+def test_rgb24_padded_and_unaligned_rows(codec, oracle):
+    """Row stride beyond width*3 (padding never read into the result); strides / bases that are only 4-byte aligned take
+    the 32-bit-load kernel and give the same bytes."""
+    w, h = 320, 64
+    img = synth_family(1, w, h)
+    want = oracle.compress(DXT1 if codec == gb.BOTH else codec, img, w, h)[1]
+    want2 = oracle.compress(ETC1, img, w, h)[1]
+    for stride, base, coop in ((w * 3 + 256, 0, True), (w * 3 + 4, 0, False), (w * 3, 4, False), (w * 3 + 52, 8, False)):
+        rc, got, got2 = rgb24_device(codec, img, w, h, stride, base)
+        assert rc == 0 and np.array_equal(got, want), (stride, base)
+        assert ("32-bit" in gb.last_launch_kernel()) == (not coop), gb.last_launch_kernel()
+        if codec == gb.BOTH:
+            assert np.array_equal(got2, want2), (stride, base)
+
+
+def test_rgb24_float_reference_flavour(reference):
+    """goofyRef-exact flavour from packed RGB, including widths that are only multiples of 4."""
+    for (w, h) in ((256, 64), (20, 8), (1028, 12)):
+        img = synth_family(1, w, h, seed=w)
+        for codec, ref_codec in ((gb.DXT1_FLOATREF, DXT1), (gb.ETC1_FLOATREF, ETC1)):
+            rc, got, _ = rgb24_device(codec, img, w, h)
+            assert rc == 0 and np.array_equal(got, reference.compress_float_reference(ref_codec, aligned_copy(img), w, h)[1]), (w, h, codec)
+
+
+def test_rgb24_uniform_batch_and_argument_checks(oracle):
+    w, h, n = 128, 64, 5
+    imgs = [synth_family(i % 4, w, h, seed=i + 1) for i in range(n)]
+    pitch = w * 3 * h + 48
+    buf = np.zeros(n * pitch, dtype=np.uint8)
+    for i, im in enumerate(imgs):
+        buf[i * pitch: i * pitch + w * 3 * h] = rgb_of(im, w, h).reshape(-1)
+    d_src = dev(buf)
+    out_pitch = w * h // 2 + 64
+    d_a = torch.zeros(n * out_pitch, dtype=torch.uint8, device="cuda")
+    d_b = torch.zeros(n * out_pitch, dtype=torch.uint8, device="cuda")
+    gb.check(gb.encode_rgb24_device(gb.BOTH, d_a, d_src, w, h, w * 3, d_result2=d_b, input_image_pitch=pitch,
+                                    result_image_pitch=out_pitch, n_images=n))
+    torch.cuda.synchronize()
+    a, b = d_a.cpu().numpy(), d_b.cpu().numpy()
+    for i, im in enumerate(imgs):
+        assert np.array_equal(a[i * out_pitch: i * out_pitch + w * h // 2], oracle.compress(DXT1, im, w, h)[1]), i
+        assert np.array_equal(b[i * out_pitch: i * out_pitch + w * h // 2], oracle.compress(ETC1, im, w, h)[1]), i
+    # the codec's own shape rules, then the packed-row rules
+    assert gb.encode_rgb24_device(DXT1, d_a, d_src, 24, 32, 72) == -1
+    assert gb.encode_rgb24_device(DXT1, d_a, d_src, 32, 30, 96) == -2
+    assert gb.encode_rgb24_device(DXT1, d_a, d_src, 0, 0, 0) == 0
+    assert gb.encode_rgb24_device(DXT1, d_a, d_src, 32, 32, 95) == -5      # stride < width*3
+    assert gb.encode_rgb24_device(DXT1, d_a, d_src, 32, 32, 98) == -4      # stride % 4
+    assert gb.encode_rgb24_device(DXT1, d_a, 0, 32, 32, 96) == -3
+    assert gb.encode_rgb24_device(gb.BOTH, d_a, d_src, 32, 32, 96) == -3   # no second result
+    assert gb.encode_rgb24_device(7, d_a, d_src, 32, 32, 96) == -6
+    assert gb.encode_rgb24_device(DXT1, d_a, d_src, w, h, w * 3, input_image_pitch=w * 3, result_image_pitch=out_pitch, n_images=2) == -8
+
+
+def test_rgb24_all_test_images(oracle):
+    names = image_names()
+    if not names:
+        pytest.skip("oracle/_ref/test-data not present")
+    for n in names[::3]:
+        img = load_test_image(n)
+        h, w = img.shape[:2]
+        for codec in CODECS:
+            rc, got, _ = rgb24_device(codec, img, w, h)
+            assert rc == 0 and np.array_equal(got, oracle.compress(codec, img, w, h)[1]), n
+
+
+# ------------------------------------------------------------------ host path: alpha-stripped staging
+@pytest.fixture()
+def rgb_mode():
+    before = gb.get_host_rgb_staging()
+    yield
+    gb.set_host_rgb_staging(before)
+
+
+def _pinned(a):
+    t = torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).pin_memory()
+    return t
+
+
+@pytest.mark.parametrize("mode", [gb.HOST_RGB_OFF, gb.HOST_RGB_AUTO, gb.HOST_RGB_ALWAYS])
+def test_host_path_same_bytes_in_every_staging_mode(mode, rgb_mode, reference):
+    """Pageable and pinned buffers, small (zero-copy) and large (hybrid: raw strips from the front, alpha-stripped strips
+    from the back) images, padded stride, random alpha: every mode returns the reference's bytes."""
+    assert gb.set_host_rgb_staging(mode) in (0, 1, 2)
+    assert gb.get_host_rgb_staging() == mode
+    cases = [(768, 512, 0), (2048, 2048, 0), (4096, 3072, 512), (8192, 2048, 0)]
+    for (w, h, pad) in cases:
+        stride = w * 4 + pad
+        tight = splitmix_rgba(w * h, seed=w + h + mode).reshape(h, w * 4)
+        padded = np.full((h, stride), 0xAB, dtype=np.uint8)
+        padded[:, : w * 4] = tight
+        want = {c: reference.compress_mt(c, aligned_copy(padded), w, h, stride, 8)[1] for c in CODECS}
+        before = gb.host_link_stats()
+        for codec, fn in ((DXT1, gb.compressDXT1), (ETC1, gb.compressETC1)):
+            out = np.zeros(w * h // 2, dtype=np.uint8)
+            assert fn(out, aligned_copy(padded), w, h, stride) == 0           # pageable
+            assert np.array_equal(out, want[codec]), (mode, w, h, codec, "pageable")
+            t_in, t_out = _pinned(padded), torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory()
+            assert fn(t_out, t_in, w, h, stride) == 0                         # pinned
+            assert np.array_equal(t_out.numpy(), want[codec]), (mode, w, h, codec, "pinned")
+        # both codecs from one upload
+        a, b = torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory(), torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory()
+        assert gb.encode_dual_host(a, b, _pinned(padded), w, h, stride) == 0
+        assert np.array_equal(a.numpy(), want[DXT1]) and np.array_equal(b.numpy(), want[ETC1]), (mode, w, h, "dual pinned")
+        a2, b2 = np.zeros(w * h // 2, dtype=np.uint8), np.zeros(w * h // 2, dtype=np.uint8)
+        assert gb.encode_dual_host(a2, b2, aligned_copy(padded), w, h, stride) == 0
+        assert np.array_equal(a2, want[DXT1]) and np.array_equal(b2, want[ETC1]), (mode, w, h, "dual pageable")
+        after = gb.host_link_stats()
+        sent = after["bytes_uploaded"] - before["bytes_uploaded"]
+        full = 6 * w * h * 4       # six host calls
+        if mode == gb.HOST_RGB_OFF:
+            assert sent == full and after["packed_strips"] == before["packed_strips"]
+        else:
+            assert sent < full     # pageable calls always strip the alpha byte
+        if mode == gb.HOST_RGB_ALWAYS and w * h * 4 > 32 << 20:
+            assert after["raw_strips"] == before["raw_strips"] and after["packed_strips"] > before["packed_strips"]
+
+
+def test_host_path_float_reference_and_batch_with_rgb_staging(rgb_mode, reference):
+    gb.set_host_rgb_staging(gb.HOST_RGB_AUTO)
+    for (w, h) in ((20, 8), (1028, 64), (4096, 2560)):
+        img = aligned_copy(synth_family(1, w, h, seed=w + 3))
+        for fn, codec in ((gb.goofyRef.compressDXT1, DXT1), (gb.goofyRef.compressETC1, ETC1)):
+            want = reference.compress_float_reference(codec, img, w, h)[1]
+            out = np.zeros(w * h // 2, dtype=np.uint8)
+            assert fn(out, img, w, h, w * 4) == 0
+            assert np.array_equal(out, want), (w, h, codec, "pageable")
+            t_out = torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory()
+            assert fn(t_out, _pinned(img), w, h, w * 4) == 0
+            assert np.array_equal(t_out.numpy(), want), (w, h, codec, "pinned")
+    # a host batch mixing small pageable images and one large pinned image (which takes the hybrid scheduler mid-batch)
+    shapes = [(256, 128), (4096, 2304), (768, 512), (64, 16)]
+    imgs = [aligned_copy(synth_family(i % 4, w, h, seed=i + 9)) for i, (w, h) in enumerate(shapes)]
+    srcs = [aligned_copy(im) if i != 1 else _pinned(im) for i, im in enumerate(imgs)]
+    outs = [np.zeros(w * h // 2, dtype=np.uint8) if i != 1 else torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory()
+            for i, (w, h) in enumerate(shapes)]
+    outs2 = [np.zeros(w * h // 2, dtype=np.uint8) if i != 1 else torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory()
+             for i, (w, h) in enumerate(shapes)]
+    gb.check(gb.encode_host_batch(gb.BOTH, [(s, o, w, h, w * 4, o2) for s, o, o2, (w, h) in zip(srcs, outs, outs2, shapes)]))
+    for im, o, o2, (w, h) in zip(imgs, outs, outs2, shapes):
+        o = o.numpy() if hasattr(o, "numpy") else o
+        o2 = o2.numpy() if hasattr(o2, "numpy") else o2
+        assert np.array_equal(o, reference.compress(DXT1, im, w, h)[1]) and np.array_equal(o2, reference.compress(ETC1, im, w, h)[1]), (w, h)
+
+
+def test_hybrid_scheduler_splits_the_image(rgb_mode, reference):
+    """AUTO on a large pinned image: strips leave from both ends (some raw, some alpha-stripped) and the result is the
+    reference's; the split itself depends on the host and is only reported."""
+    gb.set_host_rgb_staging(gb.HOST_RGB_AUTO)
+    w, h = 8192, 8192
+    img = torch.from_numpy(synth_family(1, w, h, seed=11).reshape(-1)).pin_memory()
+    out = torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory()
+    before = gb.host_link_stats()
+    for _ in range(3):
+        assert gb.compressDXT1(out, img, w, h, w * 4) == 0
+    after = gb.host_link_stats()
+    raw, packed = after["raw_strips"] - before["raw_strips"], after["packed_strips"] - before["packed_strips"]
+    assert raw + packed == 3 * 64   # 4 MiB strips
+    sent = after["bytes_uploaded"] - before["bytes_uploaded"]
+    assert sent == (raw * 4 + packed * 3) * (4 << 20) // 4
+    print(f"hybrid split on this host: {raw} raw + {packed} alpha-stripped strips, {gb.host_threads()} host threads")
+    want = reference.compress_mt(DXT1, aligned_copy(img.numpy()), w, h, w * 4, 16)[1]
+    assert np.array_equal(out.numpy(), want)

@@ -9,16 +9,25 @@ SRC = ROOT / "tests" / "copy_pool_stress.cpp"
 BUILD = ROOT / "tests" / "_build"
 
 
-def _build(flags, name):
+def _build(flags, name, src=SRC):
     BUILD.mkdir(exist_ok=True)
     exe = BUILD / name
-    res = subprocess.run(["g++", "-std=c++17", "-pthread", *flags, "-o", str(exe), str(SRC)], capture_output=True, text=True)
+    res = subprocess.run(["g++", "-std=c++17", "-pthread", *flags, "-o", str(exe), str(src)], capture_output=True, text=True)
     return exe if res.returncode == 0 else None
 
 
+def test_rgb_pack_rows():
+    """Alpha-stripping staging copy (goofy_b200/csrc/rgb_pack.h): scalar and SSSE3 packers write exactly the R, G, B
+    bytes of every pixel and nothing outside the packed row, at every alignment and width % 4 == 0."""
+    exe = _build(["-O2"], "rgb_pack_host", ROOT / "tests" / "rgb_pack_host.cpp")
+    assert exe is not None
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
 def test_copy_pool_stress():
-    """Spin-then-sleep wake-up handshake of CopyPool (goofy_b200/csrc/copy_pool.h): every copy of 2000 jobs of
-    varying size is checked, with pauses that let the workers fall asleep between jobs."""
+    """Spin-then-sleep wake-up handshake of CopyPool (goofy_b200/csrc/copy_pool.h): every copy (and every
+    alpha-stripping pack) of 2000 jobs of varying size is checked, with pauses that let the workers fall asleep between jobs."""
     exe = _build(["-O2"], "copy_pool_stress")
     assert exe is not None
     out = subprocess.run([str(exe), "2000"], capture_output=True, text=True, timeout=120)

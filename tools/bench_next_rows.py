@@ -70,6 +70,18 @@ for name, c in (("decode_dxt1", gb.DXT1), ("decode_etc1", gb.ETC1)):
     record(name, timed(lambda i, c=c: gb.check(gb.decode_device(c, dec[i], blk[c][i], size, size, size * 4))))
 for name, c in (("block_sse_dxt1", gb.DXT1), ("block_sse_etc1", gb.ETC1)):
     record(name, timed(lambda i, c=c: gb.check(gb.block_sse_device(c, blk[c][i], src[i], size, size, size * 4, sse))))
+# packed RGB input (3 bytes per pixel): 3.5 B/px of traffic; one launch per texture like the rows above, and all
+# textures in one batched launch like bench.py's headline
+rgb = torch.empty((n_tex, size, size, 3), dtype=torch.uint8, device="cuda")
+rgb.copy_(src[..., :3])
+out2 = torch.empty((n_tex, ob), dtype=torch.uint8, device="cuda")
+for name, c in (("encode_rgb24_dxt1", gb.DXT1), ("encode_rgb24_etc1", gb.ETC1), ("encode_rgb24_both", gb.BOTH)):
+    bpp = 4.0 if c == gb.BOTH else 3.5
+    record(name, timed(lambda i, c=c: gb.check(gb.encode_rgb24_device(c, out[i], rgb[i], size, size, size * 3, d_result2=out2[i]))), bytes_per_px=bpp)
+    record(name + "_batched", timed(lambda i, c=c: gb.check(gb.encode_rgb24_device(c, out, rgb, size, size, size * 3, d_result2=out2,
+                                                                                   input_image_pitch=px * 3, result_image_pitch=ob, n_images=n_tex))),
+           bytes_per_px=bpp, pixels=px * n_tex)
+assert torch.equal(out, blk[gb.DXT1]) and torch.equal(out2, blk[gb.ETC1]), "rgb24 results differ from the RGBA path"
 # relaxed shapes: the same texture minus 3 pixels in both directions (edge blocks replicate)
 w2 = h2 = size - 3
 for name, c in (("encode_relaxed_dxt1", gb.DXT1), ("encode_relaxed_etc1", gb.ETC1)):
