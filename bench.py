@@ -331,6 +331,11 @@ class Ctx:
             # a second, CPU-side group: ranks that merely wait for rank 0 must not do it inside an NCCL kernel that
             # spins on their GPU (rank 0 may be using that GPU through the in-library shard scheduler)
             self.host_group = dist.new_group(backend="gloo")
+        # one process per GPU on a shared host: the host path's staging threads (copy / alpha strip) are divided between
+        # the local ranks; set before the library starts its pool (an explicit GOOFY_B200_HOST_THREADS wins)
+        if self.distributed and "GOOFY_B200_HOST_THREADS" not in os.environ:
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", self.world))
+            os.environ["GOOFY_B200_HOST_THREADS"] = str(max(2, min(8, (os.cpu_count() or 8) // max(1, local_world))))
         from goofy_b200 import _lib
         self.lib = _lib.load()          # raw ctypes entry points: pointers and the stream as plain integers, so a
         self.stream = int(torch.cuda.current_stream().cuda_stream)   # 20 us launch is not waiting for Python
@@ -732,6 +737,21 @@ def run_b200_arm(args):
     value_d = px_per_step * side_steps * world / (ms_d * 1e-3) / 1e6
     dual_kernel = gb.last_launch_kernel()
 
+    # packed-RGB input (3 B/px, the data format a decoded PNG / JPEG has): same batch, same protocol, 3.5 B/px
+    rgb = torch.empty((batch, size, size, 3), dtype=torch.uint8, device=dev)
+    rgb.copy_(src[..., :3])
+    p_rgb = int(rgb.data_ptr())
+
+    def rgb24_step():
+        gb.check(lib.goofy_b200_encode_rgb24_device(codec, p_dst2, 0, p_rgb, size, size, size * 3, size * size * 3, out_bytes, batch, st))
+    ms_r, _ = timed(rgb24_step, side_steps, 3)
+    value_r = px_per_step * side_steps * world / (ms_r * 1e-3) / 1e6
+    rgb24_kernel = gb.last_launch_kernel()
+    step()
+    torch.cuda.synchronize()
+    rgb24_same = bool(torch.equal(dst, dst2))
+    del rgb
+
     # ---- end to end through the drop-in host API: pinned host buffers, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -743,14 +763,34 @@ def run_b200_arm(args):
         def e2e_step():
             gb.check(host_fn(h_dst, h_src, size, size, stride))
         e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(3):
+            e2e_step()      # the hybrid scheduler's pack-time estimate settles before the link counters are read
+        link0 = gb.host_link_stats()
         ms_e, _ = timed(e2e_step, e2e_steps, 3)
+        link1 = gb.host_link_stats()
+        calls = e2e_steps + 3   # timed() ran 3 warm-up steps after link0 was read
+        strips = (link1["raw_strips"] - link0["raw_strips"]) + (link1["packed_strips"] - link0["packed_strips"])
+        # the same call with alpha-stripped staging turned off: every pixel crosses the link as RGBA (plain DMA pipeline)
+        mode = gb.set_host_rgb_staging(gb.HOST_RGB_OFF)
+        ms_raw, _ = timed(e2e_step, e2e_steps, 3)
+        gb.set_host_rgb_staging(mode)
         pcie_ms = pcie_probe(ctx, size)
         e2e = {"value": size * size * e2e_steps * world / (ms_e * 1e-3) / 1e6, "unit": "MP/s",
-               "h2d_bytes_per_step": size * size * 4, "d2h_bytes_per_step": out_bytes,
+               # bytes that actually crossed the link per call, counted by the library (the input tensor holds 4 B/px; the
+               # host path drops the alpha byte of the strips its staging threads get to before the copy engine does)
+               "h2d_bytes_per_step": (link1["bytes_uploaded"] - link0["bytes_uploaded"]) // calls,
+               "h2d_bytes_logical": size * size * 4, "d2h_bytes_per_step": out_bytes,
                "ms_per_step": ms_e / e2e_steps,
+               "host_rgb_staging": {0: "off", 1: "auto", 2: "always"}[mode],
+               "alpha_stripped_share_of_strips": ((link1["packed_strips"] - link0["packed_strips"]) / strips) if strips else 0.0,
+               "host_threads": gb.host_threads(),
+               "rgba_dma_only": {"value": size * size * e2e_steps * world / (ms_raw * 1e-3) / 1e6, "unit": "MP/s",
+                                 "ms_per_step": ms_raw / e2e_steps, "h2d_bytes_per_step": size * size * 4,
+                                 "note": "same call, goofy_b200_set_host_rgb_staging(OFF): the plain strip pipeline of round 1"},
                "pcie_bound_ms": pcie_ms, "ms_per_step_over_pcie_bound": (ms_e / e2e_steps) / pcie_ms,
-               "pcie_bound_note": "bare pinned cudaMemcpyAsync of the same bytes (4 B/px in, 0.5 B/px out, concurrently) on this box, "
-                                  f"all {world} rank(s) at the same time, max over ranks",
+               "pcie_bound_note": "bare pinned cudaMemcpyAsync of the tensors' bytes (4 B/px in, 0.5 B/px out, concurrently) on this box, "
+                                  f"all {world} rank(s) at the same time, max over ranks; the host call can finish sooner because it "
+                                  "sends h2d_bytes_per_step, not h2d_bytes_logical",
                "api": f"goofy_b200.compress{args.codec.upper()}(result, input, w, h, stride) on pinned host buffers"}
         # both codecs from one upload (goofy_b200_encode_dual_host): 4 B/px in, 1 B/px out
         h_dual = torch.empty((2, out_bytes), dtype=torch.uint8).pin_memory()
@@ -847,6 +887,10 @@ def run_b200_arm(args):
                             "achieved_gbs_per_gpu": achieved_o, "frac": achieved_o / peak, "kernel": other_kernel},
             "dual_output": {"value": value_d, "unit": "MP/s (each pixel encoded to both DXT1 and ETC1s)",
                             "achieved_gbs_per_gpu": value_d / world * 1e6 * 5.0 / 1e9, "kernel": dual_kernel},
+            "rgb24_input": {"value": value_r, "unit": "MP/s", "bytes_per_pixel": 3.5,
+                            "achieved_gbs_per_gpu": value_r / world * 1e6 * 3.5 / 1e9, "kernel": rgb24_kernel,
+                            "same_bytes_as_rgba_path": rgb24_same,
+                            "note": "goofy_b200_encode_rgb24_device: the same textures as packed RGB8 (no alpha byte), not BASELINE.json's RGBA8 workload"},
         }
         if e2e is not None:
             line["e2e"] = e2e

@@ -31,13 +31,17 @@ public:
     // dst/src rows of `rowBytes`, `rows` of them; the calling thread takes a share of the rows too
     void copy2d(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t rows)
     {
-        job2d(dst, dstPitch, src, srcPitch, rowBytes, rows, false);
+        job2d(dst, dstPitch, src, srcPitch, rowBytes, rows, false, false);
     }
     // the same with the alpha byte dropped on the way (rgb_pack.h): src rows of `pixels` RGBA8 pixels -> dst rows of
     // pixels * 3 bytes
-    void pack2d(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t pixels, size_t rows)
+    // `streaming`: non-temporal stores.  The packed rows are read next by the DMA engine (or by the GPU over the link),
+    // never by this core, and a regular store first reads every destination line into the cache; worth it for images
+    // that do not fit the last-level cache anyway (8192^2 pageable 7.0-8.6 -> 6.1-6.6 ms, hybrid pinned 5.5 -> 4.5 ms),
+    // not for small ones, whose staged rows the link then reads straight from the cache (2048^2 321 vs 340 us; session P)
+    void pack2d(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t pixels, size_t rows, bool streaming)
     {
-        job2d(dst, dstPitch, src, srcPitch, pixels * 4u, rows, true);
+        job2d(dst, dstPitch, src, srcPitch, pixels * 4u, rows, true, streaming);
     }
     // threads that work on one job, the caller included
     size_t threads() const { return nWorkers_ + 1; }
@@ -50,14 +54,24 @@ public:
     }
 
 private:
-    void job2d(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t rows, bool pack)
+    void job2d(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t rows, bool pack, bool streaming)
     {
         if (rows * rowBytes < kPoolMinBytes || nWorkers_ == 0) {
-            run(dst, dstPitch, src, srcPitch, rowBytes, 0, rows, pack);
+            run(dst, dstPitch, src, srcPitch, rowBytes, 0, rows, pack, streaming);
             return;
         }
         std::lock_guard<std::mutex> serial(jobMutex_);  // one copy job at a time
-        dst_ = dst; dstPitch_ = dstPitch; src_ = src; srcPitch_ = srcPitch; rowBytes_ = rowBytes; rows_ = rows; pack_ = pack;
+        const size_t parts = nWorkers_ + 1;
+        publish(dst, dstPitch, src, srcPitch, rowBytes, rows, pack, streaming, parts);
+        run(dst, dstPitch, src, srcPitch, rowBytes, rows * (parts - 1) / parts, rows, pack, streaming);  // the caller's share: the last slice
+        wait_for_workers();
+    }
+    // hand rows [0, rows * nWorkers_ / parts) to the workers (jobMutex_ held)
+    void publish(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t rows, bool pack, bool streaming,
+                 size_t parts)
+    {
+        dst_ = dst; dstPitch_ = dstPitch; src_ = src; srcPitch_ = srcPitch; rowBytes_ = rowBytes; rows_ = rows; pack_ = pack; streaming_ = streaming;
+        parts_ = parts;
         pending_.store((int)nWorkers_, std::memory_order_relaxed);
         // seq_cst on both sides of the generation_ / sleepers_ handshake (store then load here, store then load in the
         // worker): at least one side sees the other's write, so a worker cannot go to sleep on a published job
@@ -66,8 +80,9 @@ private:
             { std::lock_guard<std::mutex> g(m_); }               // a worker between its predicate check and its wait
             cv_.notify_all();
         }
-        const size_t parts = nWorkers_ + 1;
-        run(dst, dstPitch, src, srcPitch, rowBytes, rows * (parts - 1) / parts, rows, pack);  // the caller's share: the last slice
+    }
+    void wait_for_workers()
+    {
         for (int spin = 0; pending_.load(std::memory_order_acquire) != 0; ++spin) {
             if (spin < 4096) { cpu_relax(); continue; }
             std::unique_lock<std::mutex> g(m_);
@@ -101,13 +116,10 @@ private:
         nWorkers_ = n;
         for (unsigned i = 0; i < n; ++i) std::thread([this, i] { loop(i); }).detach();
     }
-    static void run(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t r0, size_t r1, bool pack)
+    static void run(uint8_t* dst, size_t dstPitch, const uint8_t* src, size_t srcPitch, size_t rowBytes, size_t r0, size_t r1, bool pack, bool streaming)
     {
         if (pack) {
-            // non-temporal stores: the packed rows are read next by the DMA engine (or by the GPU over the link), never
-            // by this core, and a regular store would first read every destination line into the cache
-            static const bool nt = []() { const char* e = std::getenv("GOOFY_B200_PACK_NT"); return !(e && e[0] == '0'); }();
-            gbpack::pack_rows(dst, dstPitch, src, srcPitch, rowBytes / 4u, r0, r1, nt);
+            gbpack::pack_rows(dst, dstPitch, src, srcPitch, rowBytes / 4u, r0, r1, streaming);
             return;
         }
         if (dstPitch == rowBytes && srcPitch == rowBytes) {
@@ -130,8 +142,8 @@ private:
                 sleepers_.fetch_sub(1);
             }
             seen = generation_.load(std::memory_order_acquire);
-            const size_t parts = nWorkers_ + 1;
-            run(dst_, dstPitch_, src_, srcPitch_, rowBytes_, rows_ * index / parts, rows_ * (index + 1) / parts, pack_);
+            const size_t parts = parts_;
+            run(dst_, dstPitch_, src_, srcPitch_, rowBytes_, rows_ * index / parts, rows_ * (index + 1) / parts, pack_, streaming_);
             if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
                 std::lock_guard<std::mutex> g(m_);   // the caller may have gone to sleep on done_
                 if (callerWaiting_) done_.notify_one();
@@ -144,8 +156,8 @@ private:
     // the current job: written by the submitter before generation_ is bumped (release), read by workers after (acquire)
     uint8_t* dst_ = nullptr;
     const uint8_t* src_ = nullptr;
-    size_t dstPitch_ = 0, srcPitch_ = 0, rowBytes_ = 0, rows_ = 0;
-    bool pack_ = false;
+    size_t dstPitch_ = 0, srcPitch_ = 0, rowBytes_ = 0, rows_ = 0, parts_ = 1;
+    bool pack_ = false, streaming_ = false;
     std::atomic<int> pending_{0};
     std::atomic<int> sleepers_{0};
     std::atomic<uint64_t> generation_{0};

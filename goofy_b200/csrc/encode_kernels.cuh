@@ -383,16 +383,14 @@ __global__ void __launch_bounds__(256, CODEC == kDxt1 ? 8 : 6) encode_floatref_k
 // Packed RGB8 input: 3 bytes per pixel, no alpha byte (the encoders ignore alpha, GoofyTC/goofy_tc.h:297, so a
 // caller that holds RGB data -- a decoded PNG/JPEG, or the host path's alpha-dropping staging copy, rgb_pack.h --
 // need not widen it to RGBA first: 3.5 instead of 4.5 bytes of traffic per pixel).  A block row of one block is 12
-// bytes at a 4-byte-aligned address; the three words are widened to the four pixel words of the RGBA kernels with two
-// byte permutes and a shift.  The fourth byte of every pixel word is whatever followed it, which the arithmetic never
-// looks at (tests/test_gpu_parity.py::test_alpha_is_ignored).  Row-walking CTAs, grid.z = image of a batch.
-//
-// COOP = true (rows 16-byte aligned, width % 16 == 0): a warp's 32 blocks are 4 pixel rows x 384 contiguous bytes
-// = 96 x 16 bytes, exactly three 128-bit loads per lane.  The warp fetches them cooperatively (fully coalesced, every
-// byte requested ONCE -- which matters when the source is pinned host memory read over PCIe, where nothing caches a
-// second request for the same sector), parks them in a warp-private 1.5 KiB shared-memory tile and every lane reads its
-// 12 bytes per row back as three LDS.32 (word stride 3 across lanes: conflict-free).  Only __syncwarp, no CTA barrier.
-// COOP = false: three 32-bit global loads per row and thread (any 4-byte-aligned rows; float-reference widths).
+// bytes at a 4-byte-aligned address: three 32-bit loads (a warp covers 384 contiguous bytes per pixel row with them;
+// L1 merges the three requests per line), widened to the four pixel words of the RGBA kernels with two byte permutes
+// and a shift.  The fourth byte of every pixel word is whatever followed it, which the arithmetic never looks at
+// (tests/test_gpu_parity.py::test_alpha_is_ignored).  Row-walking CTAs, grid.z = image of a batch at fixed pitches.
+// (A warp-cooperative variant -- three coalesced 128-bit loads per lane into a warp-private shared-memory tile, read
+// back as twelve conflict-free LDS.32 -- was measured 16-19 % SLOWER on device memory, 5661 vs 6713 GB/s DXT1, and no
+// different on pinned host memory read over PCIe: the extra STS / LDS / __syncwarp instructions cost more than the
+// narrower requests; session O, profiles/r02_rgb24_sessions.md.)
 __device__ __forceinline__ uint32_t load_word(const uint8_t* p)
 {
     uint32_t v;
@@ -401,68 +399,34 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t* p)
 }
 
 // w0 = R0 G0 B0 R1 | w1 = G1 B1 R2 G2 | w2 = B2 R3 G3 B3  ->  four pixel words (byte 3 of each: don't care)
-__device__ __forceinline__ uint4 widen_rgb24(uint32_t w0, uint32_t w1, uint32_t w2)
+__device__ __forceinline__ uint4 load_row_rgb24(const uint8_t* p)
 {
+    const uint32_t w0 = load_word(p), w1 = load_word(p + 4), w2 = load_word(p + 8);
     return make_uint4(w0, prmt(w0, w1, 0x6543u), prmt(w1, w2, 0x5432u), w2 >> 8);
 }
 
-template <int MODE, int FLAVOUR, bool COOP>
+template <int MODE, int FLAVOUR>
 __global__ void __launch_bounds__(256, rgb24_ctas_per_sm(MODE)) encode_rgb24_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
-    __shared__ __align__(16) uint4 tile[COOP ? 8 : 1][COOP ? 96 : 1];   // per warp: 4 pixel rows x 384 bytes
     pdl_launch_dependents();
-    const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
-    if (MODE != kDxt1) stage_control_lut<FLAVOUR != 0, 256>(lut, t);
-    const uint32_t lane = threadIdx.x & 31u;   // blockDim.x is a multiple of 32: a warp never straddles two block rows
-    const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x, bxWarp = bx - lane;
+    if (MODE != kDxt1) stage_control_lut<FLAVOUR != 0, 256>(lut, threadIdx.y * blockDim.x + threadIdx.x);
+    const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t by = blockIdx.y * blockDim.y + threadIdx.y;
-    const uint8_t* src = P.src + (uint64_t)blockIdx.z * P.srcPitch;
+    const uint8_t* src = P.src + (uint64_t)blockIdx.z * P.srcPitch + (uint64_t)bx * 12u;
     uint8_t* dst = P.dst + (uint64_t)blockIdx.z * P.dstPitch + (uint64_t)bx * 8u;
     uint8_t* dst2 = MODE == kDual ? P.dst2 + (uint64_t)blockIdx.z * P.dstPitch + (uint64_t)bx * 8u : nullptr;
     pdl_wait();
     if (MODE != kDxt1) __syncthreads();
-    if (bxWarp >= P.bw || by >= P.bh) return;   // warp-uniform
-    const bool live = bx < P.bw;
+    if (bx >= P.bw || by >= P.bh) return;
     const uint32_t rowStep = gridDim.y * blockDim.y;
-
-    // COOP: this lane's three 16-byte chunks of the warp tile (chunk c = pixel row c / 24, column c % 24)
-    const uint32_t warpBytes = (P.bw - bxWarp < 32u ? P.bw - bxWarp : 32u) * 12u;
-    uint64_t chunkOffset[3];
-    bool chunkLive[3];
-#pragma unroll
-    for (uint32_t k = 0; k < 3u; ++k) {
-        const uint32_t c = lane + 32u * k, row = c / 24u, col = c - row * 24u;
-        chunkOffset[k] = (uint64_t)row * P.stride + (uint64_t)bxWarp * 12u + col * 16u;
-        chunkLive[k] = col * 16u < warpBytes;
-    }
-    uint4* warpTile = tile[COOP ? (t >> 5) : 0];
-    const uint32_t* mine = reinterpret_cast<const uint32_t*>(warpTile) + 3u * lane;
-
 #pragma unroll 1
     for (; by < P.bh; by += rowStep) {
         const uint8_t* s = src + (uint64_t)by * 4u * P.stride;
-        uint4 r0, r1, r2, r3;
-        if (COOP) {
-#pragma unroll
-            for (uint32_t k = 0; k < 3u; ++k)
-                if (chunkLive[k]) warpTile[lane + 32u * k] = load_row(s + chunkOffset[k]);
-            __syncwarp();
-            r0 = widen_rgb24(mine[0], mine[1], mine[2]);
-            r1 = widen_rgb24(mine[96], mine[97], mine[98]);
-            r2 = widen_rgb24(mine[192], mine[193], mine[194]);
-            r3 = widen_rgb24(mine[288], mine[289], mine[290]);
-            __syncwarp();   // the tile is rewritten in the next round
-        } else {
-            if (!live) continue;
-            s += (uint64_t)bx * 12u;
-            const uint8_t *s1 = s + P.stride, *s2 = s1 + P.stride, *s3 = s2 + P.stride;
-            r0 = widen_rgb24(load_word(s), load_word(s + 4), load_word(s + 8));
-            r1 = widen_rgb24(load_word(s1), load_word(s1 + 4), load_word(s1 + 8));
-            r2 = widen_rgb24(load_word(s2), load_word(s2 + 4), load_word(s2 + 8));
-            r3 = widen_rgb24(load_word(s3), load_word(s3 + 4), load_word(s3 + 8));
-        }
-        if (!live) continue;
+        const uint4 r0 = load_row_rgb24(s);
+        const uint4 r1 = load_row_rgb24(s + P.stride);
+        const uint4 r2 = load_row_rgb24(s + 2ull * P.stride);
+        const uint4 r3 = load_row_rgb24(s + 3ull * P.stride);
         const uint64_t o = (uint64_t)by * P.bw * 8u;
         encode_and_store_flavour<MODE, FLAVOUR>(r0, r1, r2, r3, lut, dst + o, MODE == kDual ? dst2 + o : nullptr);
     }

@@ -513,7 +513,6 @@ int encode_rgb24(int codec, void* dst, void* dst2, const void* src, uint32_t wid
     const int mode = both ? gb::kDual : (codec == GOOFY_B200_ETC1 || codec == GOOFY_B200_ETC1_FLOATREF) ? gb::kEtc1 : gb::kDxt1;
     const uint32_t resident = (uint32_t)sms * (uint32_t)gb::rgb24_ctas_per_sm(mode);
     static const uint32_t rowsEnv = (uint32_t)env_int("GOOFY_B200_RGB24_ROWS_PER_CTA", 1, 1 << 20, 0);
-    static const bool rgb24Coop = env_int("GOOFY_B200_RGB24_COOP", 0, 1, 1) != 0;   // 0: 32-bit loads everywhere (A/B runs)
     uint32_t gy = (rowGroups + (rowsEnv ? rowsEnv : 4u) - 1u) / (rowsEnv ? rowsEnv : 4u);
     const uint32_t perImage = (resident + nImages - 1u) / nImages;
     if (gy < perImage / gx) gy = perImage / gx;
@@ -527,19 +526,13 @@ int encode_rgb24(int codec, void* dst, void* dst2, const void* src, uint32_t wid
         Q.dst += (uint64_t)img0 * dstPitch;
         if (Q.dst2) Q.dst2 += (uint64_t)img0 * dstPitch;
         const dim3 grid(gx, gy, nz);
-        // warp-cooperative 128-bit loads when every pixel row starts on a 16-byte boundary; else 32-bit loads per thread
-        const bool coop = (((uintptr_t)Q.src | stride | (nz > 1u ? srcPitch : 0u)) & 15u) == 0u && width % 16u == 0u && rgb24Coop;
-#define GB_RGB24(MODE, FLAV, NAME)                                                                                              \
-    (coop ? launch_encode(gb::encode_rgb24_kernel<MODE, FLAV, true>, grid, block, stream, Q, "encode_rgb24_kernel<" NAME ">")     \
-          : launch_encode(gb::encode_rgb24_kernel<MODE, FLAV, false>, grid, block, stream, Q, "encode_rgb24_kernel[32-bit loads]<" NAME ">"))
         switch (codec) {
-            case GOOFY_B200_DXT1: rc = GB_RGB24(gb::kDxt1, 0, "dxt1"); break;
-            case GOOFY_B200_ETC1: rc = GB_RGB24(gb::kEtc1, 0, "etc1s"); break;
-            case GOOFY_B200_BOTH: rc = GB_RGB24(gb::kDual, 0, "dxt1+etc1s"); break;
-            case GOOFY_B200_DXT1_FLOATREF: rc = GB_RGB24(gb::kDxt1, 1, "dxt1, float reference"); break;
-            default: rc = GB_RGB24(gb::kEtc1, 1, "etc1s, float reference"); break;
+            case GOOFY_B200_DXT1: rc = launch_encode(gb::encode_rgb24_kernel<gb::kDxt1, 0>, grid, block, stream, Q, "encode_rgb24_kernel<dxt1>"); break;
+            case GOOFY_B200_ETC1: rc = launch_encode(gb::encode_rgb24_kernel<gb::kEtc1, 0>, grid, block, stream, Q, "encode_rgb24_kernel<etc1s>"); break;
+            case GOOFY_B200_BOTH: rc = launch_encode(gb::encode_rgb24_kernel<gb::kDual, 0>, grid, block, stream, Q, "encode_rgb24_kernel<dxt1+etc1s>"); break;
+            case GOOFY_B200_DXT1_FLOATREF: rc = launch_encode(gb::encode_rgb24_kernel<gb::kDxt1, 1>, grid, block, stream, Q, "encode_rgb24_kernel<dxt1, float reference>"); break;
+            default: rc = launch_encode(gb::encode_rgb24_kernel<gb::kEtc1, 1>, grid, block, stream, Q, "encode_rgb24_kernel<etc1s, float reference>"); break;
         }
-#undef GB_RGB24
         if (rc != GOOFY_B200_OK) return rc;
     }
     return GOOFY_B200_OK;

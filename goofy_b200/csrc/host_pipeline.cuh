@@ -43,6 +43,7 @@ int host_rgb_mode()
 // strips of pinned images sent as they were / alpha-stripped first: what a benchmark reports instead of assuming
 std::atomic<uint64_t> g_hostUploaded{0}, g_rawStrips{0}, g_packedStrips{0};
 
+constexpr size_t kStreamingPackBytes = 32u << 20;   // images beyond this are packed with non-temporal stores (copy_pool.h: pack2d)
 constexpr size_t kStagePieceBytes = 768u << 10;   // zero-copy path: smallest piece of a strip staged and encoded on its own
 constexpr size_t kCopyPieceBytes = 2u << 20;      // copying path: smallest piece of a strip staged and sent on its own
 
@@ -151,8 +152,12 @@ int make_host_job(int codec, void* result, const void* input, uint32_t width, ui
 // P = L, 0.75 from P = 4/3 L on.
 int run_hybrid(int codec, const HostJob& J, ThreadResources& R, int dev)
 {
-    static const size_t stripTarget = (size_t)env_int("GOOFY_B200_HYBRID_STRIP_KB", 256, 16384, 4096) << 10;
-    static const double linkGBs = (double)env_int("GOOFY_B200_HYBRID_LINK_GBS", 1, 1000, 50);   // only sizes the queue
+    // strips: 1/32 of the image, between 4 and 8 MiB (per-strip host work -- five API calls -- against the granularity
+    // of the split and of the tail; sessions O-R, profiles/r02_rgb24_sessions.md); GOOFY_B200_HYBRID_STRIP_KB overrides
+    static const size_t stripEnv = (size_t)env_int("GOOFY_B200_HYBRID_STRIP_KB", 256, 16384, 0) << 10;
+    static const double linkGBs = (double)env_int("GOOFY_B200_HYBRID_LINK_GBS", 1, 1000, 55);   // only sizes the queue
+    size_t stripTarget = stripEnv ? stripEnv : (size_t)J.blockRows * 4u * J.rowBytes / 32u;
+    if (!stripEnv) stripTarget = stripTarget < (4u << 20) ? (4u << 20) : stripTarget > (8u << 20) ? (8u << 20) : stripTarget;
     uint32_t stripRows = (uint32_t)(stripTarget / (J.rowBytes * 4u));
     if (stripRows == 0u) stripRows = 1u;
     const uint32_t nStrips = (J.blockRows + stripRows - 1u) / stripRows;
@@ -228,6 +233,9 @@ int run_hybrid(int codec, const HostJob& J, ThreadResources& R, int dev)
     // seconds one pack of a full strip takes: a running mean, seeded per calling thread by its previous call
     thread_local double packSeconds = 0.0;
     if (packSeconds == 0.0) packSeconds = (double)stripIn / 30e9;
+    // (A variant in which the calling thread only fed the link while the pool's workers packed asynchronously measured
+    // the same, 4420 vs 4422 us on 8192^2, as did 9 or 12 instead of 8 host threads: the packing rate of these hosts is set
+    // by their memory system, about 45 GB/s of input, not by the thread count.  Session R.)
     uint32_t front = 0, back = nStrips;
     while (front < back) {
         rc = poll();
@@ -235,18 +243,22 @@ int run_hybrid(int codec, const HostJob& J, ThreadResources& R, int dev)
         // queued upload time that covers one pack, with a margin; never less than two raw strips
         double cover = packSeconds * 1.25 * linkGBs * 1e9;
         if (cover < 2.0 * (double)stripIn) cover = 2.0 * (double)stripIn;
-        if (!packAll && (double)queuedBytes < cover && nFlights < kFlights) {
+        // the last strips go raw: a strip packed at the very end would add its pack time to the tail of the call, while a
+        // raw one only queues behind the uploads already in flight (4096^2: the hybrid call lost to plain DMA without
+        // this).  "Last" = what the link drains in the time one more pack would take.
+        const bool tail = (double)(back - front) * (double)stripIn <= cover;
+        if (!packAll && ((double)queuedBytes < cover || tail) && nFlights < kFlights) {
             rc = issue(front++, -1);
             if (rc != GOOFY_B200_OK) return fail(rc);
             continue;
         }
         int ps = 0;
         while (ps < kPackSlots && packBusy[ps]) ++ps;
-        if (ps < kPackSlots && nFlights < kFlights) {
+        if (ps < kPackSlots && nFlights < kFlights && (packAll || !tail)) {
             const uint32_t k = --back;
             const uint32_t r0 = k * stripRows, rows = J.blockRows - r0 < stripRows ? J.blockRows - r0 : stripRows;
             const auto t0 = std::chrono::steady_clock::now();
-            CopyPool::get().pack2d((uint8_t*)R.stage.pack[ps], packedRow, J.input + (size_t)r0 * 4u * J.stride, J.stride, J.width, (size_t)rows * 4u);
+            CopyPool::get().pack2d((uint8_t*)R.stage.pack[ps], packedRow, J.input + (size_t)r0 * 4u * J.stride, J.stride, J.width, (size_t)rows * 4u, true);
             const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * (double)stripRows / (double)rows;
             packSeconds = 0.75 * packSeconds + 0.25 * dt;
             packBusy[ps] = true;
@@ -317,7 +329,7 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
     };
     // stage rows [y0, y1) of a strip into pinned memory: a plain copy, or with the alpha byte dropped on the way
     auto stage_rows = [&](const HostJob& J, uint8_t* stage, const uint8_t* src, size_t rows) {
-        if (J.packIn) CopyPool::get().pack2d(stage, J.stagedRowBytes, src, J.stride, J.width, rows);
+        if (J.packIn) CopyPool::get().pack2d(stage, J.stagedRowBytes, src, J.stride, J.width, rows, (size_t)J.blockRows * 4u * J.rowBytes > kStreamingPackBytes);
         else CopyPool::get().copy2d(stage, J.rowBytes, src, J.stride, J.rowBytes, rows);
         g_hostUploaded.fetch_add(rows * J.stagedRowBytes, std::memory_order_relaxed);
     };

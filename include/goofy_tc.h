@@ -63,6 +63,18 @@ inline int encodeRelaxed(int codec, void* dResult, const void* dInput, uint32_t 
     return goofy_b200_encode_relaxed_device(codec, dResult, dInput, width, height, stride, stream);
 }
 
+// Packed RGB8 input (3 bytes per pixel, rows `stride` >= width*3 bytes apart, 4-byte aligned): the bytes the RGBA entry
+// points produce for the same pixels.  codec may be BOTH (dResult2 = the ETC1s blocks); n images at fixed pitches.
+inline int encodeRgb24(int codec, void* dResult, void* dResult2, const void* dInput, uint32_t width, uint32_t height, uint32_t stride,
+                       uint64_t inputImagePitch = 0, uint64_t resultImagePitch = 0, uint32_t nImages = 1, void* stream = nullptr)
+{
+    return goofy_b200_encode_rgb24_device(codec, dResult, dResult2, dInput, width, height, stride, inputImagePitch, resultImagePitch,
+                                          nImages, stream);
+}
+
+// Host path: drop the alpha byte while staging (GOOFY_B200_HOST_RGB_OFF / _AUTO / _ALWAYS); returns the previous mode.
+inline int setHostRgbStaging(int mode) { return goofy_b200_set_host_rgb_staging(mode); }
+
 // n images of one shape at fixed pitches.
 inline int encodeBatch(Codec codec, void* dResult, const void* dInput, uint32_t width, uint32_t height, uint32_t stride,
                        uint64_t inputImagePitch, uint64_t resultImagePitch, uint32_t nImages, void* stream = nullptr)

@@ -28,7 +28,7 @@ int main(int argc, char** argv)
         if (it % 3 == 0) {   // the alpha-stripping job (pack2d) through the same handshake: 1024 pixels per row
             const size_t pixels = rowBytes / 4u;
             std::memset(dst.data(), 0, rows * pixels * 3u);
-            CopyPool::get().pack2d(dst.data(), pixels * 3u, src.data(), pitch, pixels, rows);
+            CopyPool::get().pack2d(dst.data(), pixels * 3u, src.data(), pitch, pixels, rows, it % 2 == 0);
             for (size_t r = 0; r < rows; r += 13) {
                 const uint8_t* d = dst.data() + r * pixels * 3u;
                 const uint8_t* q = src.data() + r * pitch;

@@ -44,7 +44,7 @@ def test_rgb24_synthetic_families_vs_oracle(codec, family, oracle):
     for (w, h, seed) in ((256, 256, 1), (1024, 512, 77), (2064, 36, 5)):
         img = synth_family(family, w, h, seed=seed)
         rc, got, _ = rgb24_device(codec, img, w, h)
-        assert rc == 0 and "rgb24" in gb.last_launch_kernel() and "32-bit" not in gb.last_launch_kernel()
+        assert rc == 0 and "rgb24" in gb.last_launch_kernel()
         assert np.array_equal(got, oracle.compress(codec, img, w, h)[1]), (family, w, h)
 
 
@@ -63,16 +63,14 @@ def test_rgb24_ragged_shapes_all_outputs(shape, oracle):
 
 @pytest.mark.parametrize("codec", CODECS + [gb.BOTH])
 def test_rgb24_padded_and_unaligned_rows(codec, oracle):
-    """Row stride beyond width*3 (padding never read into the result); strides / bases that are only 4-byte aligned take
-    the 32-bit-load kernel and give the same bytes."""
+    """Row stride beyond width*3 (padding never read into the result); strides / bases that are only 4-byte aligned."""
     w, h = 320, 64
     img = synth_family(1, w, h)
     want = oracle.compress(DXT1 if codec == gb.BOTH else codec, img, w, h)[1]
     want2 = oracle.compress(ETC1, img, w, h)[1]
-    for stride, base, coop in ((w * 3 + 256, 0, True), (w * 3 + 4, 0, False), (w * 3, 4, False), (w * 3 + 52, 8, False)):
+    for stride, base in ((w * 3 + 256, 0), (w * 3 + 4, 0), (w * 3, 4), (w * 3 + 52, 8)):
         rc, got, got2 = rgb24_device(codec, img, w, h, stride, base)
         assert rc == 0 and np.array_equal(got, want), (stride, base)
-        assert ("32-bit" in gb.last_launch_kernel()) == (not coop), gb.last_launch_kernel()
         if codec == gb.BOTH:
             assert np.array_equal(got2, want2), (stride, base)
 
@@ -219,9 +217,10 @@ def test_hybrid_scheduler_splits_the_image(rgb_mode, reference):
         assert gb.compressDXT1(out, img, w, h, w * 4) == 0
     after = gb.host_link_stats()
     raw, packed = after["raw_strips"] - before["raw_strips"], after["packed_strips"] - before["packed_strips"]
-    assert raw + packed == 3 * 64   # 4 MiB strips
+    assert raw > 0 and (raw + packed) % 3 == 0 and 3 * 16 <= raw + packed <= 3 * 128   # strips of 2 .. 16 MiB
+    strip = 3 * w * h * 4 // (raw + packed)
     sent = after["bytes_uploaded"] - before["bytes_uploaded"]
-    assert sent == (raw * 4 + packed * 3) * (4 << 20) // 4
+    assert sent == raw * strip + packed * strip * 3 // 4
     print(f"hybrid split on this host: {raw} raw + {packed} alpha-stripped strips, {gb.host_threads()} host threads")
     want = reference.compress_mt(DXT1, aligned_copy(img.numpy()), w, h, w * 4, 16)[1]
     assert np.array_equal(out.numpy(), want)
