@@ -88,9 +88,9 @@ def host_threads() -> int:
 
 def host_link_stats() -> dict:
     """Bytes the host path sent host -> device so far, and raw / alpha-stripped strips of large pinned images."""
-    b, r, p = C.c_uint64(), C.c_uint64(), C.c_uint64()
-    _lib.load().goofy_b200_host_link_stats(C.byref(b), C.byref(r), C.byref(p))
-    return {"bytes_uploaded": b.value, "raw_strips": r.value, "packed_strips": p.value}
+    b, r, p, pc, nc = (C.c_uint64() for _ in range(5))
+    _lib.load().goofy_b200_host_link_stats(C.byref(b), C.byref(r), C.byref(p), C.byref(pc), C.byref(nc))
+    return {"bytes_uploaded": b.value, "raw_strips": r.value, "packed_strips": p.value, "packing_calls": pc.value, "plain_calls": nc.value}
 
 
 def output_bytes(width: int, height: int) -> int:

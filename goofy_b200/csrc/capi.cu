@@ -69,8 +69,11 @@ int goofy_b200_get_host_rgb_staging(void) { return host_rgb_mode(); }
 
 int goofy_b200_host_threads(void) { return (int)CopyPool::get().threads(); }
 
-void goofy_b200_host_link_stats(uint64_t* bytes_uploaded, uint64_t* raw_strips, uint64_t* packed_strips)
+void goofy_b200_host_link_stats(uint64_t* bytes_uploaded, uint64_t* raw_strips, uint64_t* packed_strips, uint64_t* packing_calls,
+                                uint64_t* plain_calls)
 {
+    if (packing_calls) *packing_calls = g_packingCalls.load(std::memory_order_relaxed);
+    if (plain_calls) *plain_calls = g_plainCalls.load(std::memory_order_relaxed);
     if (bytes_uploaded) *bytes_uploaded = g_hostUploaded.load(std::memory_order_relaxed);
     if (raw_strips) *raw_strips = g_rawStrips.load(std::memory_order_relaxed);
     if (packed_strips) *packed_strips = g_packedStrips.load(std::memory_order_relaxed);

@@ -41,7 +41,7 @@ int host_rgb_mode()
 }
 // bytes that crossed the link host -> device through the host path (copy engine or zero-copy kernel reads), and
 // strips of pinned images sent as they were / alpha-stripped first: what a benchmark reports instead of assuming
-std::atomic<uint64_t> g_hostUploaded{0}, g_rawStrips{0}, g_packedStrips{0};
+std::atomic<uint64_t> g_hostUploaded{0}, g_rawStrips{0}, g_packedStrips{0}, g_packingCalls{0}, g_plainCalls{0};
 
 constexpr size_t kStreamingPackBytes = 32u << 20;   // images beyond this are packed with non-temporal stores (copy_pool.h: pack2d)
 constexpr size_t kStagePieceBytes = 768u << 10;   // zero-copy path: smallest piece of a strip staged and encoded on its own
@@ -150,8 +150,44 @@ int make_host_job(int codec, void* result, const void* input, uint32_t width, ui
 // plenty sends nearly everything packed.  With packing rate P and link rate L (input bytes per second) the share of
 // packed strips settles at x = 1 / (L / P + 1/4) (capped at 1) and the call takes x / P: 0.8 of the plain time at
 // P = L, 0.75 from P = 4/3 L on.
+//
+// That holds while the LINK is what bounds the call.  With one process per GPU on a shared host the host's memory
+// system can be the bound instead (an 8-GPU box delivers 27-35 GB/s per GPU with four ranks uploading, well below the
+// link rate), and packing, which moves 2.5 bytes through host memory per input byte where plain DMA moves one, then
+// makes everybody slower (4 ranks: -12...-18 %, sessions S and T).  A process cannot find that out by comparing its own
+// calls with and without packing: the cost of its packing falls on the OTHER ranks, so each of them measures packing
+// as the better reply to what the others do, and all of them settle on the worse state (tried: session T).  What a
+// process can see is the rate of its own PLAIN uploads: a B200 link (PCIe Gen5 x16) carries a plain call at 53-54
+// GB/s of input when nothing else holds it back, so AUTO packs only while its plain calls reach kHybridMinPlainGBs
+// (GOOFY_B200_HYBRID_MIN_LINK_GBS) and -- belt and braces -- while calls that pack measure faster than calls that do
+// not.  Every thread's first two calls are plain (the first one cold and not recorded); later every sixteenth call
+// runs the way that is NOT preferred to keep both means current.  The bytes produced are the same either way.
+constexpr int kHybridMinPlainGBs = 48;
+struct HybridChoice {
+    double ratePacking = 0.0, ratePlain = 0.0;   // input bytes per second, running means; 0 = not measured yet
+    uint32_t calls = 0;
+    bool next()   // true: this call packs
+    {
+        static const double minPlain = (double)env_int("GOOFY_B200_HYBRID_MIN_LINK_GBS", 0, 1000, kHybridMinPlainGBs) * 1e9;
+        const uint32_t n = calls++;
+        if (n < 2u) return false;              // the first call is cold (page tables, clocks): measured, not recorded
+        if (ratePlain < minPlain) return false;   // something other than the link bounds this process's uploads
+        if (ratePacking == 0.0) return true;
+        const bool preferred = ratePacking > ratePlain;
+        return (n & 15u) == 15u ? !preferred : preferred;   // every sixteenth call refreshes the other mean
+    }
+    void record(bool packed, double bytesPerSecond)
+    {
+        if (calls <= 1u) return;
+        double& r = packed ? ratePacking : ratePlain;
+        r = r == 0.0 ? bytesPerSecond : 0.5 * r + 0.5 * bytesPerSecond;
+    }
+};
+thread_local HybridChoice t_hybridChoice;
+
 int run_hybrid(int codec, const HostJob& J, ThreadResources& R, int dev)
 {
+    const int mode = host_rgb_mode();
     // strips: 1/32 of the image, between 4 and 8 MiB (per-strip host work -- five API calls -- against the granularity
     // of the split and of the tail; sessions O-R, profiles/r02_rgb24_sessions.md); GOOFY_B200_HYBRID_STRIP_KB overrides
     static const size_t stripEnv = (size_t)env_int("GOOFY_B200_HYBRID_STRIP_KB", 256, 16384, 0) << 10;
@@ -170,6 +206,7 @@ int run_hybrid(int codec, const HostJob& J, ThreadResources& R, int dev)
     if (rc != GOOFY_B200_OK) return rc;
     rc = R.stage.ensure_pack(stripPacked);
     if (rc != GOOFY_B200_OK) return rc;
+    const auto callStart = std::chrono::steady_clock::now();   // (after the one-time allocations of a thread's first call)
 
     struct Flight { bool busy = false; size_t bytes = 0; int packSlot = -1; } flight[kFlights];
     bool packBusy[kPackSlots] = {};
@@ -229,7 +266,7 @@ int run_hybrid(int codec, const HostJob& J, ThreadResources& R, int dev)
         return GOOFY_B200_OK;
     };
 
-    const bool packAll = host_rgb_mode() == 2;
+    const bool packAll = mode == 2;
     // seconds one pack of a full strip takes: a running mean, seeded per calling thread by its previous call
     thread_local double packSeconds = 0.0;
     if (packSeconds == 0.0) packSeconds = (double)stripIn / 30e9;
@@ -274,6 +311,9 @@ int run_hybrid(int codec, const HostJob& J, ThreadResources& R, int dev)
         const cudaError_t e = cudaStreamSynchronize(R.pipe.stream[i]);
         if (e != cudaSuccess) return fail(cuda_rc(e));
     }
+    if (mode != 2)
+        t_hybridChoice.record(true, (double)J.blockRows * 4.0 * (double)J.rowBytes /
+                                           std::chrono::duration<double>(std::chrono::steady_clock::now() - callStart).count());
     return GOOFY_B200_OK;
 }
 
@@ -455,19 +495,30 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
     };
 
     int slot = 0;
+    bool plainTimed = false;
+    std::chrono::steady_clock::time_point plainStart;
     for (uint32_t j = 0; j < nJobs; ++j) {
         const HostJob& J = jobs[j];
-        // large pinned images (the ones that would go through the copy engine strip by strip): the hybrid scheduler
+        // large pinned images (the ones that go through the copy engine strip by strip): with alpha-stripped strips from
+        // the back (run_hybrid) when AUTO's measurements say so; otherwise the plain strip pipeline below, timed for them
         if (!J.stageIn && !J.stageOut && !J.stageOut2 && J.blockRows != 0u && host_rgb_mode() != 0 &&
             (size_t)J.blockRows * 4u * J.rowBytes > zeroCopyMax) {
-            for (int i = 0; i < kSlots; ++i, slot = (slot + 1) % kSlots) {
-                rc = retire(slot);
-                if (rc != GOOFY_B200_OK) return fail(rc);
+            const bool packing = host_rgb_mode() == 2 || t_hybridChoice.next();
+            (packing ? g_packingCalls : g_plainCalls).fetch_add(1, std::memory_order_relaxed);
+            if (packing) {
+                for (int i = 0; i < kSlots; ++i, slot = (slot + 1) % kSlots) {
+                    rc = retire(slot);
+                    if (rc != GOOFY_B200_OK) return fail(rc);
+                }
+                rc = run_hybrid(codec, J, R, dev);
+                if (rc != GOOFY_B200_OK) return rc;
+                t_trace.mark("hybrid pinned image done");
+                continue;
             }
-            rc = run_hybrid(codec, J, R, dev);
-            if (rc != GOOFY_B200_OK) return rc;
-            t_trace.mark("hybrid pinned image done");
-            continue;
+            if (nJobs == 1u) {
+                plainTimed = true;
+                plainStart = std::chrono::steady_clock::now();
+            }
         }
         for (uint32_t r0 = 0; r0 < J.blockRows; r0 += J.stripRows, slot = (slot + 1) % kSlots) {
             const uint32_t rows = J.blockRows - r0 < J.stripRows ? J.blockRows - r0 : J.stripRows;
@@ -480,6 +531,9 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         rc = retire(slot);
         if (rc != GOOFY_B200_OK) return fail(rc);
     }
+    if (plainTimed)
+        t_hybridChoice.record(false, (double)jobs[0].blockRows * 4.0 * (double)jobs[0].rowBytes /
+                                         std::chrono::duration<double>(std::chrono::steady_clock::now() - plainStart).count());
     t_trace.mark("done");
     t_trace.end();
     return GOOFY_B200_OK;

@@ -106,8 +106,9 @@ int goofy_b200_get_load_path(void);
  * are input).  Process-wide; set returns the previous setting (or GOOFY_B200_E_ARGS).
  *   OFF     every pixel crosses the link as RGBA
  *   AUTO    (default) pageable input is staged as packed RGB -- the staging copy is made anyway; large pinned input is
- *           split between plain DMA and alpha-stripped strips according to how fast the host's cores pack (a host with
- *           none to spare degrades to plain DMA)
+ *           split between plain DMA and alpha-stripped strips according to how fast the host's cores pack, and only
+ *           while calls that pack measure faster than calls that do not (one process per GPU on a shared host can be
+ *           bound by host memory instead of by the link; packing then loses and AUTO stops doing it)
  *   ALWAYS  every strip of a large pinned image is alpha-stripped first (experiments)
  * The bytes produced are identical in every mode.  Environment: GOOFY_B200_HOST_RGB=0|1|2 (initial mode),
  * GOOFY_B200_HOST_THREADS=n (host threads per staging job, the caller included; default min(8, cores / 2)). */
@@ -119,9 +120,10 @@ int goofy_b200_get_host_rgb_staging(void);
 /* Host threads that work on one staging job (copy or alpha strip), the calling thread included. */
 int goofy_b200_host_threads(void);
 /* What the host path sent over the link so far in this process (all threads): bytes host -> device (copy engine and
- * zero-copy kernel reads), and strips of large pinned images sent as they were / alpha-stripped first.  Any pointer
- * may be NULL. */
-void goofy_b200_host_link_stats(uint64_t* bytes_uploaded, uint64_t* raw_strips, uint64_t* packed_strips);
+ * zero-copy kernel reads); strips of large pinned images sent as they were / alpha-stripped first; calls on large pinned
+ * images that ran with packing / as plain DMA (AUTO measures both and uses the faster).  Any pointer may be NULL. */
+void goofy_b200_host_link_stats(uint64_t* bytes_uploaded, uint64_t* raw_strips, uint64_t* packed_strips,
+                                uint64_t* packing_calls, uint64_t* plain_calls);
 
 /* ---- drop-in host-pointer API: same arguments, order and return codes as the reference ---- */
 int goofy_b200_compress_dxt1(unsigned char* result, const unsigned char* input, unsigned int width,

@@ -206,21 +206,26 @@ def test_host_path_float_reference_and_batch_with_rgb_staging(rgb_mode, referenc
 
 
 def test_hybrid_scheduler_splits_the_image(rgb_mode, reference):
-    """AUTO on a large pinned image: strips leave from both ends (some raw, some alpha-stripped) and the result is the
-    reference's; the split itself depends on the host and is only reported."""
-    gb.set_host_rgb_staging(gb.HOST_RGB_AUTO)
+    """A large pinned image with packing forced (ALWAYS) and under AUTO (which packs only where its own measurements say
+    it pays: the first two calls of a thread are plain DMA): the result is the reference's either way; the split itself
+    depends on the host and is only reported."""
     w, h = 8192, 8192
     img = torch.from_numpy(synth_family(1, w, h, seed=11).reshape(-1)).pin_memory()
-    out = torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory()
-    before = gb.host_link_stats()
-    for _ in range(3):
-        assert gb.compressDXT1(out, img, w, h, w * 4) == 0
-    after = gb.host_link_stats()
-    raw, packed = after["raw_strips"] - before["raw_strips"], after["packed_strips"] - before["packed_strips"]
-    assert raw > 0 and (raw + packed) % 3 == 0 and 3 * 16 <= raw + packed <= 3 * 128   # strips of 2 .. 16 MiB
-    strip = 3 * w * h * 4 // (raw + packed)
-    sent = after["bytes_uploaded"] - before["bytes_uploaded"]
-    assert sent == raw * strip + packed * strip * 3 // 4
-    print(f"hybrid split on this host: {raw} raw + {packed} alpha-stripped strips, {gb.host_threads()} host threads")
     want = reference.compress_mt(DXT1, aligned_copy(img.numpy()), w, h, w * 4, 16)[1]
-    assert np.array_equal(out.numpy(), want)
+    for mode, calls in ((gb.HOST_RGB_AUTO, 5), (gb.HOST_RGB_ALWAYS, 1)):
+        gb.set_host_rgb_staging(mode)
+        before = gb.host_link_stats()
+        for _ in range(calls):
+            out = torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory()
+            assert gb.compressDXT1(out, img, w, h, w * 4) == 0
+            assert np.array_equal(out.numpy(), want), mode
+        after = gb.host_link_stats()
+        d = {k: after[k] - before[k] for k in after}
+        assert d["packing_calls"] + d["plain_calls"] == calls
+        assert d["bytes_uploaded"] <= calls * w * h * 4
+        if mode == gb.HOST_RGB_ALWAYS:
+            assert d["packing_calls"] == 1 and d["raw_strips"] == 0 and d["packed_strips"] >= 16
+            assert d["bytes_uploaded"] == w * h * 3
+        else:
+            assert d["plain_calls"] >= 2
+        print(f"mode {mode}: {d}, {gb.host_threads()} host threads")

@@ -14,9 +14,9 @@ out_pageable = np.zeros(W * H // 2, dtype=np.uint8)
 pin_in = torch.empty(img.size, dtype=torch.uint8).pin_memory(); pin_in.numpy()[:] = img
 pin_out = torch.empty(W * H // 2, dtype=torch.uint8).pin_memory()
 def bench(name, dst, src):
-    for _ in range(3): gb.check(gb.compressDXT1(dst, src, W, H, W * 4))
+    for _ in range(6): gb.check(gb.compressDXT1(dst, src, W, H, W * 4))
     ts = []
-    for _ in range(5 if W * H > (1 << 22) else 200):
+    for _ in range(24 if W * H > (1 << 22) else 200):
         t0 = time.perf_counter(); gb.check(gb.compressDXT1(dst, src, W, H, W * 4)); ts.append(time.perf_counter() - t0)
     best, med = min(ts), sorted(ts)[len(ts) // 2]
     print(f"{W}x{H} {name:28s} best {best*1e6:9.1f} us  median {med*1e6:9.1f} us  {W*H/best/1e6:9.0f} MP/s")
