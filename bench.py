@@ -779,8 +779,9 @@ def run_b200_arm(args):
 
     # ---- end to end through the drop-in host API: pinned host buffers, H2D + D2H inside the timed region.  Run after
     #      the clock sampler has stopped: its child process queries NVML back to back, and every query holds a driver lock
-    #      that the host path's own driver calls (copies, launches, event queries: dozens per call) then wait for -- the
-    #      same call measured 4.39 ms on its own and 5.07 ms with the sampler running (round 2, session T)
+    #      that the host path's own driver calls (copies, launches, event queries: dozens per call) then wait for (the
+    #      call averaged 5.07 ms with the sampler running and 4.66-4.76 ms after it had stopped, against 4.36-4.45 ms from
+    #      a C++ caller on the same boxes; round 2, sessions T and U)
     e2e = None
     if not args.no_e2e:
         h_src = torch.empty((size, size, 4), dtype=torch.uint8).pin_memory()

@@ -57,7 +57,13 @@ constexpr int ctas_per_sm(int mode) { return mode == 0 ? GB_CTAS_DXT1 : mode == 
 #ifndef GB_RGB24_CTAS_DXT1
 #define GB_RGB24_CTAS_DXT1 6
 #endif
-constexpr int rgb24_ctas_per_sm(int mode) { return mode == 0 ? GB_RGB24_CTAS_DXT1 : ctas_per_sm(mode); }
+#ifndef GB_RGB24_CTAS_ETC1
+#define GB_RGB24_CTAS_ETC1 GB_CTAS_ETC1
+#endif
+#ifndef GB_RGB24_CTAS_DUAL
+#define GB_RGB24_CTAS_DUAL 5   // 5418 -> 5615 GB/s against 6 (session V); DXT1 at 5 / 7 / 8: 6401 / 6096 / 6096 against 6815 at 6
+#endif
+constexpr int rgb24_ctas_per_sm(int mode) { return mode == 0 ? GB_RGB24_CTAS_DXT1 : mode == 1 ? GB_RGB24_CTAS_ETC1 : GB_RGB24_CTAS_DUAL; }
 
 struct EncodeParams {
     const uint8_t* src;
@@ -399,6 +405,9 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t* p)
 }
 
 // w0 = R0 G0 B0 R1 | w1 = G1 B1 R2 G2 | w2 = B2 R3 G3 B3  ->  four pixel words (byte 3 of each: don't care)
+// (The same widening as IMAD.HI + IMAD on the multiply pipe -- funnel shifts are multiplications by run-time powers of
+// two -- takes the twelve instructions off the integer ALU pipe, which ncu shows 74-78 % busy in these kernels, and
+// measured 2-3 % SLOWER: session W.)
 __device__ __forceinline__ uint4 load_row_rgb24(const uint8_t* p)
 {
     const uint32_t w0 = load_word(p), w1 = load_word(p + 4), w2 = load_word(p + 8);

@@ -513,7 +513,10 @@ int encode_rgb24(int codec, void* dst, void* dst2, const void* src, uint32_t wid
     const int mode = both ? gb::kDual : (codec == GOOFY_B200_ETC1 || codec == GOOFY_B200_ETC1_FLOATREF) ? gb::kEtc1 : gb::kDxt1;
     const uint32_t resident = (uint32_t)sms * (uint32_t)gb::rgb24_ctas_per_sm(mode);
     static const uint32_t rowsEnv = (uint32_t)env_int("GOOFY_B200_RGB24_ROWS_PER_CTA", 1, 1 << 20, 0);
-    uint32_t gy = (rowGroups + (rowsEnv ? rowsEnv : 4u) - 1u) / (rowsEnv ? rowsEnv : 4u);
+    // block rows per CTA (session V, 4 x 8192^2): DXT1 6449 / 6719 / 6817 / 6843 / 6799 GB/s at 2 / 3 / 4 / 6 / 8, ETC1s 5362 / 5551 /
+    // 5646 / 5736 / 5727, both 5233 / 5324 / 5418 / 5456 / 5566
+    const uint32_t rowsPerCta = rowsEnv ? rowsEnv : mode == gb::kDual ? 8u : mode == gb::kEtc1 ? 6u : 4u;
+    uint32_t gy = (rowGroups + rowsPerCta - 1u) / rowsPerCta;
     const uint32_t perImage = (resident + nImages - 1u) / nImages;
     if (gy < perImage / gx) gy = perImage / gx;
     if (gy == 0u) gy = 1u;
