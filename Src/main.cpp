@@ -18,7 +18,8 @@
 //   nvcc -x cu -gencode arch=compute_100a,code=sm_100a -Iinclude Src/main.cpp -Lgoofy_b200 -lgoofy_b200
 //
 //   goofy_bench [--codec dxt1|etc1|both] [--size 8192] [--textures 4] [--gpus N] [--iters 20]
-//               [--stride-pad 0] [--host-iters 3]                                  synthetic textures
+//               [--stride-pad 0] [--host-iters 3] [--rgb24]                        synthetic textures
+//               (--rgb24: every pass also from packed RGB8 copies of the textures, bytes compared)
 //   goofy_bench --images DIR [--list a,b,c] [--host-iters 128] [--iters 200] [--csv FILE] [--cpu-ref LIB.so] [--save-dir DIR]
 //                                                                                  the reference's image list
 #include <cuda_runtime.h>
@@ -84,6 +85,18 @@ __global__ void fill_texture_kernel(uint8_t* dst, uint32_t width, uint32_t heigh
     *reinterpret_cast<uchar4*>(dst + (size_t)y * stride + (size_t)x * 4) = p;
 }
 
+// RGBA8 rows -> packed RGB8 rows (the input of goofy::b200::encodeRgb24): harness data preparation only
+__global__ void strip_alpha_kernel(uint8_t* dst, const uint8_t* src, uint32_t width, uint32_t height, uint32_t srcStride)
+{
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= width || y >= height) return;
+    const uchar4 p = *reinterpret_cast<const uchar4*>(src + (size_t)y * srcStride + (size_t)x * 4);
+    uint8_t* d = dst + ((size_t)y * width + x) * 3;
+    d[0] = p.x;
+    d[1] = p.y;
+    d[2] = p.z;
+}
+
 static uint64_t fnv1a(const uint8_t* p, size_t n)
 {
     uint64_t h = 1469598103934665603ull;
@@ -98,6 +111,7 @@ struct Options {
     // image-list mode
     std::string imageDir, list, csv, cpuRef, saveDir;
     bool hostItersGiven = false, itersGiven = false;
+    bool rgb24 = false;   // also run every pass from packed RGB8 copies of the textures
 };
 
 struct Shard {
@@ -108,6 +122,8 @@ struct Shard {
     uint64_t* sse = nullptr;
     cudaStream_t stream = nullptr;
     float ms[3] = {0, 0, 0};        // dxt1, etc1, dual (device time of `iters` passes)
+    float msRgb[3] = {0, 0, 0};     // the same from packed RGB8 input (--rgb24)
+    bool rgbSame = true;            // ... and its bytes equal the RGBA path's
     uint64_t sseHost[2][3] = {};
     std::vector<uint64_t> hash[2];
 };
@@ -133,10 +149,11 @@ static Options parse(int argc, char** argv)
         else if (a == "--gpus") o.gpus = std::atoi(next());
         else if (a == "--iters") { o.iters = (uint32_t)std::atoi(next()); o.itersGiven = true; }
         else if (a == "--stride-pad") o.stridePad = (uint32_t)std::atoi(next());
+        else if (a == "--rgb24") o.rgb24 = true;
         else if (a == "--host-iters") { o.hostIters = (uint32_t)std::atoi(next()); o.hostItersGiven = true; }
         else {
             std::fprintf(stderr, "usage: goofy_bench [--codec dxt1|etc1|both] [--size N] [--textures K] [--gpus G] [--iters I] "
-                                 "[--stride-pad BYTES] [--host-iters I]\n"
+                                 "[--stride-pad BYTES] [--host-iters I] [--rgb24]\n"
                                  "       goofy_bench --images DIR [--list a,b,c] [--host-iters 128] [--iters 200] [--csv FILE] [--cpu-ref LIB.so] "
                                  "[--save-dir DIR]\n");
             std::exit(1);
@@ -416,6 +433,32 @@ int main(int argc, char** argv)
             if (g == 0) t1[mode] = std::chrono::steady_clock::now();
         }
 
+        // ---- the same textures as packed RGB8 (3 bytes per pixel, tight rows) through goofy::b200::encodeRgb24
+        uint8_t* rgb = nullptr;
+        uint8_t* rgbOut[2] = {nullptr, nullptr};
+        const size_t rgbBytes = (size_t)W * H * 3;
+        if (opt.rgb24 && s.count) {
+            CK(cudaMalloc(&rgb, s.count * rgbBytes));
+            CK(cudaMalloc(&rgbOut[0], s.count * outBytes));
+            CK(cudaMalloc(&rgbOut[1], s.count * outBytes));
+            for (uint32_t i = 0; i < s.count; ++i)
+                strip_alpha_kernel<<<dim3((W + 255) / 256, H), 256, 0, s.stream>>>(rgb + (size_t)i * rgbBytes, s.src + (size_t)i * imgBytes, W, H, stride);
+            CK(cudaGetLastError());
+            for (int mode = 0; mode < 3; ++mode) {
+                if (!(mode < 2 ? doCodec[mode] : doDual)) continue;
+                auto pass = [&]() {
+                    GK(goofy::b200::encodeRgb24(mode, rgbOut[mode == 1 ? 1 : 0], mode == 2 ? rgbOut[1] : nullptr, rgb, W, H, W * 3, rgbBytes, outBytes,
+                                                s.count, s.stream));
+                };
+                for (int k = 0; k < 3; ++k) pass();
+                CK(cudaEventRecord(e0, s.stream));
+                for (uint32_t k = 0; k < opt.iters; ++k) pass();
+                CK(cudaEventRecord(e1, s.stream));
+                CK(cudaStreamSynchronize(s.stream));
+                CK(cudaEventElapsedTime(&s.msRgb[mode], e0, e1));
+            }
+        }
+
         // ---- quality and identity of the results, computed where the data lives
         std::vector<uint8_t> host(outBytes);
         for (int c = 0; c < 2; ++c) {
@@ -431,8 +474,21 @@ int main(int argc, char** argv)
                 CK(cudaStreamSynchronize(s.stream));
                 s.hash[c].push_back(fnv1a(host.data(), outBytes));
             }
+            if (rgb) {   // packed-RGB input must give the same bytes
+                GK(goofy::b200::encodeRgb24(c, rgbOut[c], nullptr, rgb, W, H, W * 3, rgbBytes, outBytes, s.count, s.stream));
+                for (uint32_t i = 0; i < s.count; ++i) {
+                    CK(cudaMemcpyAsync(host.data(), rgbOut[c] + (size_t)i * outBytes, outBytes, cudaMemcpyDeviceToHost, s.stream));
+                    CK(cudaStreamSynchronize(s.stream));
+                    s.rgbSame = s.rgbSame && fnv1a(host.data(), outBytes) == s.hash[c][i];
+                }
+            }
         }
         CK(cudaStreamSynchronize(s.stream));
+        if (rgb) {
+            CK(cudaFree(rgb));
+            CK(cudaFree(rgbOut[0]));
+            CK(cudaFree(rgbOut[1]));
+        }
     };
 
     std::vector<std::thread> pool;
@@ -453,6 +509,20 @@ int main(int argc, char** argv)
         std::printf(", \"%s\": {\"mp_per_s\": %.1f, \"device_ms_max\": %.4f, \"wall_ms\": %.4f, \"gb_per_s_per_gpu\": %.1f, "
                     "\"frac_of_8TBs\": %.4f}",
                     names[mode], mps, msMax, wallS * 1e3, mps * 1e6 * bytesPerPx[mode] / 1e9 / G, mps * 1e6 * bytesPerPx[mode] / 1e9 / G / 8000.0);
+    }
+    if (opt.rgb24) {
+        const double rgbBytesPerPx[3] = {3.5, 3.5, 4.0};
+        bool same = true;
+        for (auto& s : shards) same = same && s.rgbSame;
+        std::printf(", \"rgb24_input\": {\"equals_rgba_path\": %s", same ? "true" : "false");
+        for (int mode = 0; mode < 3; ++mode) {
+            if (!(mode < 2 ? doCodec[mode] : doDual)) continue;
+            float msMax = 0;
+            for (auto& s : shards) msMax = std::max(msMax, s.msRgb[mode]);
+            const double mps = totalPx * opt.iters / (msMax * 1e-3) / 1e6;
+            std::printf(", \"%s\": {\"mp_per_s\": %.1f, \"gb_per_s_per_gpu\": %.1f}", names[mode], mps, mps * 1e6 * rgbBytesPerPx[mode] / 1e9 / G);
+        }
+        std::printf("}");
     }
     for (int c = 0; c < 2; ++c) {
         if (!doCodec[c]) continue;
@@ -505,8 +575,14 @@ int main(int argc, char** argv)
                 if (k) best = std::min(best, us);
             }
             const bool same = shards[0].count && fnv1a(hdst, outBytes) == shards[0].hash[c][0];
-            std::printf(", \"host_api_%s\": {\"mp_per_s\": %.1f, \"best_us\": %.1f, \"equals_device_path\": %s}", names[c],
-                        ((double)W * H / (best / 1e6)) / 1e6, best, same ? "true" : "false");
+            uint64_t up0 = 0, up1 = 0;   // bytes the host path sent over the link for one more call (alpha-stripped strips send 3/4)
+            goofy_b200_host_link_stats(&up0, nullptr, nullptr, nullptr, nullptr);
+            GK(fns[c](hdst, hsrc, W, H, stride));
+            goofy_b200_host_link_stats(&up1, nullptr, nullptr, nullptr, nullptr);
+            std::printf(", \"host_api_%s\": {\"mp_per_s\": %.1f, \"best_us\": %.1f, \"equals_device_path\": %s, \"h2d_bytes_last_call\": %llu, "
+                        "\"h2d_bytes_logical\": %llu}",
+                        names[c], ((double)W * H / (best / 1e6)) / 1e6, best, same ? "true" : "false", (unsigned long long)(up1 - up0),
+                        (unsigned long long)W * H * 4ull);
         }
         CK(cudaFreeHost(hsrc));
         CK(cudaFreeHost(hdst));

@@ -3,6 +3,7 @@
 #pragma once
 #include "host_resources.cuh"
 #include "copy_pool.h"
+#include "hybrid_choice.h"
 
 namespace {
 
@@ -162,28 +163,7 @@ int make_host_job(int codec, void* result, const void* input, uint32_t width, ui
 // (GOOFY_B200_HYBRID_MIN_LINK_GBS) and -- belt and braces -- while calls that pack measure faster than calls that do
 // not.  Every thread's first two calls are plain (the first one cold and not recorded); later every sixteenth call
 // runs the way that is NOT preferred to keep both means current.  The bytes produced are the same either way.
-constexpr int kHybridMinPlainGBs = 48;
-struct HybridChoice {
-    double ratePacking = 0.0, ratePlain = 0.0;   // input bytes per second, running means; 0 = not measured yet
-    uint32_t calls = 0;
-    bool next()   // true: this call packs
-    {
-        static const double minPlain = (double)env_int("GOOFY_B200_HYBRID_MIN_LINK_GBS", 0, 1000, kHybridMinPlainGBs) * 1e9;
-        const uint32_t n = calls++;
-        if (n < 2u) return false;              // the first call is cold (page tables, clocks): measured, not recorded
-        if (ratePlain < minPlain) return false;   // something other than the link bounds this process's uploads
-        if (ratePacking == 0.0) return true;
-        const bool preferred = ratePacking > ratePlain;
-        return (n & 15u) == 15u ? !preferred : preferred;   // every sixteenth call refreshes the other mean
-    }
-    void record(bool packed, double bytesPerSecond)
-    {
-        if (calls <= 1u) return;
-        double& r = packed ? ratePacking : ratePlain;
-        r = r == 0.0 ? bytesPerSecond : 0.5 * r + 0.5 * bytesPerSecond;
-    }
-};
-thread_local HybridChoice t_hybridChoice;
+thread_local HybridChoice t_hybridChoice{(double)env_int("GOOFY_B200_HYBRID_MIN_LINK_GBS", 0, 1000, kHybridMinPlainGBs) * 1e9};
 
 int run_hybrid(int codec, const HostJob& J, ThreadResources& R, int dev)
 {

@@ -738,3 +738,30 @@ def test_relaxed_shapes_edge_replication(codec, flavour, oracle):
     assert np.array_equal(d_dst.cpu().numpy(), gpu_device(gcodec, img, 256, 64)[1])
     assert gb.encode_relaxed_device(gcodec, d_dst, dev(img), 0, 0, 0) == 0
     assert gb.encode_relaxed_device(gcodec, d_dst, dev(img), 10, 10, 36) == -5
+
+
+@pytest.mark.parametrize("codec", CODECS)
+@pytest.mark.parametrize("flavour", ["sse2", "floatref"])
+def test_relaxed_shapes_aligned_rows_interior_and_edge_blocks(codec, flavour, oracle):
+    """16-byte-aligned rows: interior blocks take the 128-bit loads, the last block column / row the clamped ones.  Same
+    expectation as above, padded strides, every combination of partial right column / partial bottom row, widths on both
+    sides of a warp and of a CTA, and nothing written past the result."""
+    rng = np.random.default_rng(1234)
+    gcodec = codec if flavour == "sse2" else {DXT1: gb.DXT1_FLOATREF, ETC1: gb.ETC1_FLOATREF}[codec]
+    shapes = [(17, 9, 80), (30, 31, 128), (64, 61, 256), (61, 64, 256), (127, 5, 512), (129, 130, 528), (259, 6, 1040),
+              (1025, 3, 4112), (1021, 1023, 4096), (1024, 1022, 4096), (4099, 17, 16400), (8189, 61, 32768)]
+    for (w, h, stride) in shapes:
+        img = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+        rows = np.full((h, stride), 0xAB, dtype=np.uint8)
+        rows[:, : w * 4] = img.reshape(h, w * 4)
+        bw, bh = (w + 3) // 4, (h + 3) // 4
+        pw, ph = (w + 15) // 16 * 16, bh * 4
+        padded = np.pad(img, ((0, ph - h), (0, pw - w), (0, 0)), mode="edge")
+        full = (oracle.compress(codec, padded, pw, ph) if flavour == "sse2" else oracle.compress_float_reference(codec, padded, pw, ph))[1]
+        want = full.reshape(ph // 4, pw // 4, 8)[:, :bw].reshape(-1)
+        d_dst = torch.full((bw * bh * 8 + 64,), 0x5A, dtype=torch.uint8, device="cuda")
+        assert gb.encode_relaxed_device(gcodec, d_dst, dev(rows), w, h, stride) == 0
+        torch.cuda.synchronize()
+        got = d_dst.cpu().numpy()
+        assert np.array_equal(got[: bw * bh * 8], want), (w, h, stride)
+        assert (got[bw * bh * 8:] == 0x5A).all(), (w, h, stride)   # nothing written past the result

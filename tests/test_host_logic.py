@@ -25,6 +25,15 @@ def test_rgb_pack_rows():
     assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
 
 
+def test_hybrid_choice_policy():
+    """When the host path packs large pinned images (goofy_b200/csrc/hybrid_choice.h): link-bound single process yes,
+    shared host below link rate never, packing slower than plain only as a probe."""
+    exe = _build(["-O2"], "hybrid_choice_host", ROOT / "tests" / "hybrid_choice_host.cpp")
+    assert exe is not None
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
 def test_copy_pool_stress():
     """Spin-then-sleep wake-up handshake of CopyPool (goofy_b200/csrc/copy_pool.h): every copy (and every
     alpha-stripping pack) of 2000 jobs of varying size is checked, with pauses that let the workers fall asleep between jobs."""
