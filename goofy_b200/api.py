@@ -69,7 +69,7 @@ def get_load_path() -> int:
     return int(_lib.load().goofy_b200_get_load_path())
 
 
-HOST_RGB_OFF, HOST_RGB_AUTO, HOST_RGB_ALWAYS = 0, 1, 2
+HOST_RGB_OFF, HOST_RGB_AUTO, HOST_RGB_ALWAYS, HOST_RGB_PAGEABLE = 0, 1, 2, 3
 
 
 def set_host_rgb_staging(mode: int) -> int:

@@ -59,7 +59,7 @@ int goofy_b200_get_load_path(void) { return g_loadPath.load(std::memory_order_re
 
 int goofy_b200_set_host_rgb_staging(int mode)
 {
-    if (mode < GOOFY_B200_HOST_RGB_OFF || mode > GOOFY_B200_HOST_RGB_ALWAYS) return GOOFY_B200_E_ARGS;
+    if (mode < GOOFY_B200_HOST_RGB_OFF || mode > GOOFY_B200_HOST_RGB_PAGEABLE) return GOOFY_B200_E_ARGS;
     const int before = host_rgb_mode();
     g_hostRgb.store(mode, std::memory_order_relaxed);
     return before;

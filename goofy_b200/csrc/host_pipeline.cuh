@@ -27,7 +27,8 @@ bool is_pageable(const void* p)
     return pageable;
 }
 
-// Alpha-stripped staging (rgb_pack.h): 0 = never, 1 = AUTO, 2 = every strip of a pinned image too (experiments).
+// Alpha-stripped staging (rgb_pack.h): 0 = never, 1 = AUTO, 2 = every strip of a pinned image too (experiments),
+// 3 = pageable input only (what a launcher that runs one process per GPU on a shared host should set).
 // AUTO: pageable input is staged as packed RGB (the staging copy has to be made anyway; it then writes, and the link
 // then carries, 3 bytes per pixel instead of 4); large pinned input goes through the hybrid scheduler (run_hybrid).
 std::atomic<int> g_hostRgb{-1};
@@ -35,7 +36,7 @@ int host_rgb_mode()
 {
     int m = g_hostRgb.load(std::memory_order_relaxed);
     if (m < 0) {
-        m = env_int("GOOFY_B200_HOST_RGB", 0, 2, 1);
+        m = env_int("GOOFY_B200_HOST_RGB", 0, 3, 1);
         g_hostRgb.store(m, std::memory_order_relaxed);
     }
     return m;
@@ -159,7 +160,7 @@ int make_host_job(int codec, void* result, const void* input, uint32_t width, ui
 // calls with and without packing: the cost of its packing falls on the OTHER ranks, so each of them measures packing
 // as the better reply to what the others do, and all of them settle on the worse state (tried: session T).  What a
 // process can see is the rate of its own PLAIN uploads: a B200 link (PCIe Gen5 x16) carries a plain call at 53-54
-// GB/s of input when nothing else holds it back, so AUTO packs only while its plain calls reach kHybridMinPlainGBs
+// GB/s of input when nothing else holds it back, so AUTO packs only while its plain calls reach kHybridMinPlainGBs (48 GB/s)
 // (GOOFY_B200_HYBRID_MIN_LINK_GBS) and -- belt and braces -- while calls that pack measure faster than calls that do
 // not.  Every thread's first two calls are plain (the first one cold and not recorded); later every sixteenth call
 // runs the way that is NOT preferred to keep both means current.  The bytes produced are the same either way.
@@ -481,7 +482,8 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         const HostJob& J = jobs[j];
         // large pinned images (the ones that go through the copy engine strip by strip): with alpha-stripped strips from
         // the back (run_hybrid) when AUTO's measurements say so; otherwise the plain strip pipeline below, timed for them
-        if (!J.stageIn && !J.stageOut && !J.stageOut2 && J.blockRows != 0u && host_rgb_mode() != 0 &&
+        if (!J.stageIn && !J.stageOut && !J.stageOut2 && J.blockRows != 0u &&
+            (host_rgb_mode() == GOOFY_B200_HOST_RGB_AUTO || host_rgb_mode() == GOOFY_B200_HOST_RGB_ALWAYS) &&
             (size_t)J.blockRows * 4u * J.rowBytes > zeroCopyMax) {
             const bool packing = host_rgb_mode() == 2 || t_hybridChoice.next();
             (packing ? g_packingCalls : g_plainCalls).fetch_add(1, std::memory_order_relaxed);

@@ -110,11 +110,15 @@ int goofy_b200_get_load_path(void);
  *           while calls that pack measure faster than calls that do not (one process per GPU on a shared host can be
  *           bound by host memory instead of by the link; packing then loses and AUTO stops doing it)
  *   ALWAYS  every strip of a large pinned image is alpha-stripped first (experiments)
- * The bytes produced are identical in every mode.  Environment: GOOFY_B200_HOST_RGB=0|1|2 (initial mode),
+ *   PAGEABLE  pageable input only; pinned input always goes plain DMA.  What a launcher that runs ONE PROCESS PER GPU
+ *           on a shared host should set: the packing of one rank loads the host memory all ranks upload from, which
+ *           no rank can see in its own measurements (2 ranks: +6 % on one box, -12 % on another; 4 ranks -12...-18 %)
+ * The bytes produced are identical in every mode.  Environment: GOOFY_B200_HOST_RGB=0|1|2|3 (initial mode),
  * GOOFY_B200_HOST_THREADS=n (host threads per staging job, the caller included; default min(8, cores / 2)). */
 #define GOOFY_B200_HOST_RGB_OFF 0
 #define GOOFY_B200_HOST_RGB_AUTO 1
 #define GOOFY_B200_HOST_RGB_ALWAYS 2
+#define GOOFY_B200_HOST_RGB_PAGEABLE 3
 int goofy_b200_set_host_rgb_staging(int mode);
 int goofy_b200_get_host_rgb_staging(void);
 /* Host threads that work on one staging job (copy or alpha strip), the calling thread included. */

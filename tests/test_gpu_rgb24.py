@@ -139,11 +139,12 @@ def _pinned(a):
     return t
 
 
-@pytest.mark.parametrize("mode", [gb.HOST_RGB_OFF, gb.HOST_RGB_AUTO, gb.HOST_RGB_ALWAYS])
+@pytest.mark.parametrize("mode", [gb.HOST_RGB_OFF, gb.HOST_RGB_AUTO, gb.HOST_RGB_ALWAYS, gb.HOST_RGB_PAGEABLE])
 def test_host_path_same_bytes_in_every_staging_mode(mode, rgb_mode, reference):
     """Pageable and pinned buffers, small (zero-copy) and large (hybrid: raw strips from the front, alpha-stripped strips
     from the back) images, padded stride, random alpha: every mode returns the reference's bytes."""
-    assert gb.set_host_rgb_staging(mode) in (0, 1, 2)
+    assert gb.set_host_rgb_staging(mode) in (0, 1, 2, 3)
+    assert gb.set_host_rgb_staging(7) == -8 and gb.get_host_rgb_staging() == mode
     assert gb.get_host_rgb_staging() == mode
     cases = [(768, 512, 0), (2048, 2048, 0), (4096, 3072, 512), (8192, 2048, 0)]
     for (w, h, pad) in cases:
@@ -174,6 +175,9 @@ def test_host_path_same_bytes_in_every_staging_mode(mode, rgb_mode, reference):
             assert sent == full and after["packed_strips"] == before["packed_strips"]
         else:
             assert sent < full     # pageable calls always strip the alpha byte
+        if mode == gb.HOST_RGB_PAGEABLE:
+            assert after["packed_strips"] == before["packed_strips"] and after["packing_calls"] == before["packing_calls"]
+            assert sent == 6 * w * h * 4 - 3 * w * h     # the three pageable calls strip the alpha byte, the pinned ones do not
         if mode == gb.HOST_RGB_ALWAYS and w * h * 4 > 32 << 20:
             assert after["raw_strips"] == before["raw_strips"] and after["packed_strips"] > before["packed_strips"]
 
