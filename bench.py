@@ -841,6 +841,18 @@ def run_b200_arm(args):
         e2e["dual_output_host_call"] = {"value": size * size * e2e_steps * world / (ms_d2 * 1e-3) / 1e6,
                                         "unit": "MP/s (each pixel to DXT1 AND ETC1s, one upload)", "ms_per_step": ms_d2 / e2e_steps,
                                         "d2h_bytes_per_step": 2 * out_bytes}
+        # a caller whose pixels are packed RGB8 to begin with (goofy_b200_encode_rgb24_host): 3 B/px cross the link, no host work
+        h_rgb = torch.empty((size, size, 3), dtype=torch.uint8).pin_memory()
+        h_rgb.copy_(keep_src[..., :3])
+        h_dst3 = torch.empty((out_bytes,), dtype=torch.uint8).pin_memory()
+
+        def e2e_rgb_step():
+            gb.check(gb.encode_rgb24_host(codec, h_dst3, h_rgb, size, size, size * 3))
+        ms_r3, _ = timed(e2e_rgb_step, e2e_steps, 3)
+        e2e["rgb24_host_call"] = {"value": size * size * e2e_steps * world / (ms_r3 * 1e-3) / 1e6, "unit": "MP/s", "ms_per_step": ms_r3 / e2e_steps,
+                                  "h2d_bytes_per_step": size * size * 3, "same_bytes": bool(torch.equal(h_dst3, keep_want)),
+                                  "note": "the same texture held as packed RGB8 on the host (not BASELINE.json's RGBA8 workload)"}
+        del h_rgb, h_dst3
         # same call with ordinary (pageable) numpy buffers: the library stages them through pinned strips
         p_srcbuf = keep_src.numpy().reshape(-1)
         p_dstbuf = np.zeros(out_bytes, dtype=np.uint8)

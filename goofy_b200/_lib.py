@@ -47,6 +47,7 @@ PROTOTYPES = {
     "goofy_b200_compress_etc1_floatref": (_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_uint]),
     "goofy_b200_encode_host": (_int, [_int, _vp, _vp, _u32, _u32, _u32]),
     "goofy_b200_encode_dual_host": (_int, [_vp, _vp, _vp, _u32, _u32, _u32]),
+    "goofy_b200_encode_rgb24_host": (_int, [_int, _vp, _vp, _vp, _u32, _u32, _u32]),
     "goofy_b200_encode_host_batch": (_int, [_int, C.POINTER(GoofyB200Image), _u32]),
     "goofy_b200_encode_device": (_int, [_int, _vp, _vp, _u32, _u32, _u32, _vp]),
     "goofy_b200_encode_rgb24_device": (_int, [_int, _vp, _vp, _vp, _u32, _u32, _u32, _u64, _u64, _u32, _vp]),

@@ -177,6 +177,13 @@ def encode_dual_host(result_dxt1, result_etc1, input, width: int, height: int, s
                                                        _host_ptr(input, False), width, height, stride))
 
 
+def encode_rgb24_host(codec: int, result, input, width: int, height: int, stride: int, result2=None) -> int:
+    """A host image of packed RGB8 pixels (3 bytes per pixel, rows `stride` >= width*3 bytes apart): 3 instead of 4 input
+    bytes per pixel cross PCIe.  codec may be BOTH (result2 = the ETC1s blocks)."""
+    return int(_lib.load().goofy_b200_encode_rgb24_host(codec, _host_ptr(result, True), _host_ptr(result2, True) if result2 is not None else 0,
+                                                        _host_ptr(input, False), width, height, stride))
+
+
 def encode_host_batch(codec: int, images) -> int:
     """images: iterable of (input, result, width, height, stride[, result2]) with HOST buffers (numpy uint8 arrays or pinned
     torch tensors); codec BOTH needs result2 (the ETC1s blocks).  One pipeline for all of them: copies and kernels of

@@ -120,6 +120,12 @@ int goofy_b200_encode_dual_host(void* result_dxt1, void* result_etc1, const void
     return encode_dual_host(result_dxt1, result_etc1, input, width, height, stride);
 }
 
+int goofy_b200_encode_rgb24_host(int codec, void* result, void* result2, const void* input, uint32_t width, uint32_t height,
+                                 uint32_t stride)
+{
+    return encode_rgb24_host(codec, result, result2, input, width, height, stride);
+}
+
 int goofy_b200_encode_host_batch(int codec, const GoofyB200Image* images, uint32_t n_images)
 {
     return encode_host_batch(codec, images, n_images);

@@ -92,6 +92,8 @@ struct HostJob {
     size_t rowBytes = 0, outRowBytes = 0;
     bool stageIn = false, stageOut = false;
     bool packIn = false;      // pageable input staged as packed RGB (3 bytes per pixel) and encoded by the rgb24 kernels
+    bool rgbSource = false;   // the caller's pixels ARE packed RGB (goofy_b200_encode_rgb24_host): nothing to strip
+    bool rgbKernels() const { return packIn || rgbSource; }
     size_t stagedRowBytes = 0;   // bytes per pixel row as staged / uploaded: rowBytes, or width * 3 when packIn
 };
 
@@ -118,26 +120,36 @@ uint32_t strip_rows_for(size_t rowBytes, uint32_t height)
 
 // The argument checks of one host image, in the reference's order (goofy_tc.h:1500-1508) and then the new ones.
 // Returns GOOFY_B200_OK with job.blockRows == 0 for an empty image.
-int make_host_job(int codec, void* result, const void* input, uint32_t width, uint32_t height, uint32_t stride, HostJob& job)
+int make_host_job(int codec, void* result, const void* input, uint32_t width, uint32_t height, uint32_t stride, HostJob& job,
+                  bool rgbSource = false)
 {
-    int rc = is_floatref(codec) ? check_shape_floatref(width, height, stride) : check_shape(width, height, stride);
+    int rc = GOOFY_B200_OK;
+    if (rgbSource) {   // packed RGB rows: the codec's own shape rules, 4-byte-aligned rows of at least width * 3 bytes
+        if (width % (is_floatref(codec) ? 4u : 16u) != 0u) return GOOFY_B200_E_WIDTH;
+        if (height % 4u != 0u) return GOOFY_B200_E_HEIGHT;
+        if (width != 0u && height != 0u && (uint64_t)stride < (uint64_t)width * 3u) return GOOFY_B200_E_STRIDE;
+        if (width != 0u && height != 0u && (stride & 3u) != 0u) return GOOFY_B200_E_ALIGN;
+    } else {
+        rc = is_floatref(codec) ? check_shape_floatref(width, height, stride) : check_shape(width, height, stride);
+    }
     if (rc != GOOFY_B200_OK) return rc;
     job = HostJob();
     if (width == 0u || height == 0u) return GOOFY_B200_OK;
     if (!result || !input) return GOOFY_B200_E_NULL;
-    if (((uintptr_t)input & 15u) != 0u) return GOOFY_B200_E_ALIGN;  // the reference's aligned-load contract
+    if (((uintptr_t)input & (rgbSource ? 3u : 15u)) != 0u) return GOOFY_B200_E_ALIGN;  // RGBA: the reference's aligned-load contract
     job.input = (const uint8_t*)input;
     job.result = (uint8_t*)result;
     job.width = width;
     job.stride = stride;
-    job.rowBytes = (size_t)width * 4u;
+    job.rgbSource = rgbSource;
+    job.rowBytes = (size_t)width * (rgbSource ? 3u : 4u);
     job.outRowBytes = (size_t)(width / 4u) * 8u;
     job.blockRows = height / 4u;
     job.stripRows = strip_rows_for(job.rowBytes, height);
     // Pinned buffers are DMA'd in place; pageable ones go through the pinned staging strips.
     job.stageIn = is_pageable(input);
     job.stageOut = is_pageable(result);
-    job.packIn = job.stageIn && host_rgb_mode() != 0;
+    job.packIn = !rgbSource && job.stageIn && host_rgb_mode() != 0;
     job.stagedRowBytes = job.packIn ? (size_t)width * 3u : job.rowBytes;
     return GOOFY_B200_OK;
 }
@@ -344,7 +356,7 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
     };
     // The encode launch of one strip (or one piece of it): both codecs when the job has a second result.
     auto launch = [&](const HostJob& J, uint8_t* out, uint8_t* out2, const uint8_t* in, uint32_t pixelRows, uint32_t stride, cudaStream_t s) -> int {
-        if (J.packIn) return encode_rgb24(J.result2 ? GOOFY_B200_BOTH : codec, out, out2, in, J.width, pixelRows, stride, 0, 0, 1, s);
+        if (J.rgbKernels()) return encode_rgb24(J.result2 ? GOOFY_B200_BOTH : codec, out, out2, in, J.width, pixelRows, stride, 0, 0, 1, s);
         return J.result2 ? encode_uniform(gb::kDual, out, out2, in, J.width, pixelRows, stride, 0, 0, 1, s)
                          : encode_any(codec, out, in, J.width, pixelRows, stride, 0, 0, 1, s);
     };
@@ -482,7 +494,7 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         const HostJob& J = jobs[j];
         // large pinned images (the ones that go through the copy engine strip by strip): with alpha-stripped strips from
         // the back (run_hybrid) when AUTO's measurements say so; otherwise the plain strip pipeline below, timed for them
-        if (!J.stageIn && !J.stageOut && !J.stageOut2 && J.blockRows != 0u &&
+        if (!J.rgbSource && !J.stageIn && !J.stageOut && !J.stageOut2 && J.blockRows != 0u &&
             (host_rgb_mode() == GOOFY_B200_HOST_RGB_AUTO || host_rgb_mode() == GOOFY_B200_HOST_RGB_ALWAYS) &&
             (size_t)J.blockRows * 4u * J.rowBytes > zeroCopyMax) {
             const bool packing = host_rgb_mode() == 2 || t_hybridChoice.next();
@@ -531,6 +543,26 @@ int encode_host(int codec, void* result, const void* input, uint32_t width, uint
     rc = ensure_device_ready(&dev);
     if (rc != GOOFY_B200_OK) return rc;
     return run_host_jobs(codec, &job, 1, dev);
+}
+
+// A host image whose pixels are packed RGB8 to begin with: 3 bytes per pixel cross the link without any host-side work.
+// codec may be GOOFY_B200_BOTH (result2 = the ETC1s blocks).
+int encode_rgb24_host(int codec, void* result, void* result2, const void* input, uint32_t width, uint32_t height, uint32_t stride)
+{
+    const bool both = codec == GOOFY_B200_BOTH;
+    if (!both && !is_codec(codec)) return GOOFY_B200_E_CODEC;
+    HostJob job;
+    int rc = make_host_job(both ? GOOFY_B200_DXT1 : codec, result, input, width, height, stride, job, true);
+    if (rc != GOOFY_B200_OK || job.blockRows == 0u) return rc;
+    if (both) {
+        if (!result2) return GOOFY_B200_E_NULL;
+        job.result2 = (uint8_t*)result2;
+        job.stageOut2 = is_pageable(result2);
+    }
+    int dev = -1;
+    rc = ensure_device_ready(&dev);
+    if (rc != GOOFY_B200_OK) return rc;
+    return run_host_jobs(both ? GOOFY_B200_DXT1 : codec, &job, 1, dev);
 }
 
 // Both codecs from one upload of a host image: 4 B/px over the link instead of 8.

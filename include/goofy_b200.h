@@ -150,6 +150,14 @@ int goofy_b200_encode_host(int codec, void* result, const void* input, uint32_t 
 int goofy_b200_encode_dual_host(void* result_dxt1, void* result_etc1, const void* input, uint32_t width, uint32_t height,
                                 uint32_t stride);
 
+/* A host image of packed RGB8 pixels (3 bytes per pixel, rows `stride` >= width*3 bytes apart; input and stride 4-byte
+ * aligned): 3 instead of 4 input bytes per pixel cross PCIe with no host-side work at all -- for callers whose decoder
+ * delivers RGB (the reference's own loader widens to RGBA and sets alpha to 0xFF, Src/main.cpp:328-335, only because
+ * its encoders want 16-byte pixels groups).  Same bytes as the RGBA calls on the same pixels.  codec: GOOFY_B200_DXT1,
+ * _ETC1, _BOTH (result2 = the ETC1s blocks, ignored otherwise) or a float-reference flavour. */
+int goofy_b200_encode_rgb24_host(int codec, void* result, void* result2, const void* input, uint32_t width, uint32_t height,
+                                 uint32_t stride);
+
 /* n host images (src / dst / dst2 are HOST pointers here, `device` is ignored; codec may be GOOFY_B200_BOTH) through one pipeline on the calling thread's
  * current device: the copies and kernels of neighbouring images overlap, which a loop of single-image calls (each of
  * which waits for its own result) cannot do -- the host-side batch for the reference harness's per-image loop

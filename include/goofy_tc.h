@@ -72,6 +72,13 @@ inline int encodeRgb24(int codec, void* dResult, void* dResult2, const void* dIn
                                           nImages, stream);
 }
 
+// A HOST image of packed RGB8 pixels: 3 instead of 4 input bytes per pixel cross PCIe (resultEtc1 only with BOTH).
+inline int encodeRgb24Host(int codec, unsigned char* result, unsigned char* resultEtc1, const unsigned char* input, uint32_t width,
+                           uint32_t height, uint32_t stride)
+{
+    return goofy_b200_encode_rgb24_host(codec, result, resultEtc1, input, width, height, stride);
+}
+
 // Host path: drop the alpha byte while staging (GOOFY_B200_HOST_RGB_OFF / _AUTO / _ALWAYS); returns the previous mode.
 inline int setHostRgbStaging(int mode) { return goofy_b200_set_host_rgb_staging(mode); }
 

@@ -233,3 +233,40 @@ def test_hybrid_scheduler_splits_the_image(rgb_mode, reference):
         else:
             assert d["plain_calls"] >= 2
         print(f"mode {mode}: {d}, {gb.host_threads()} host threads")
+
+
+def test_rgb24_host_call(reference):
+    """goofy_b200_encode_rgb24_host: packed-RGB HOST images, pageable and pinned, small (zero-copy) and large (copy-engine
+    strips), padded rows, one and both codecs, float-reference flavour: the reference's bytes for the same pixels."""
+    for (w, h, pad) in ((768, 512, 0), (320, 64, 52), (2048, 2048, 0), (4096, 3072, 256)):
+        img = splitmix_rgba(w * h, seed=3 * w + h).reshape(h, w, 4)
+        stride = w * 3 + pad
+        rows = rgb_of(img, w, h, stride)
+        want = {c: reference.compress_mt(c, aligned_copy(img), w, h, w * 4, 8)[1] for c in CODECS}
+        for codec in CODECS:
+            out = np.zeros(w * h // 2, dtype=np.uint8)
+            assert gb.encode_rgb24_host(codec, out, rows.reshape(-1), w, h, stride) == 0          # pageable
+            assert np.array_equal(out, want[codec]), (w, h, codec, "pageable")
+            t_out = torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory()
+            assert gb.encode_rgb24_host(codec, t_out, _pinned(rows), w, h, stride) == 0            # pinned
+            assert np.array_equal(t_out.numpy(), want[codec]), (w, h, codec, "pinned")
+        a, b = torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory(), np.zeros(w * h // 2, dtype=np.uint8)
+        before = gb.host_link_stats()["bytes_uploaded"]
+        assert gb.encode_rgb24_host(gb.BOTH, a, _pinned(rows), w, h, stride, result2=b) == 0
+        assert gb.host_link_stats()["bytes_uploaded"] - before == w * h * 3
+        assert np.array_equal(a.numpy(), want[DXT1]) and np.array_equal(b, want[ETC1]), (w, h, "both")
+    w, h = 1028, 64
+    img = aligned_copy(synth_family(1, w, h, seed=5)).reshape(h, w, 4)
+    out = np.zeros(w * h // 2, dtype=np.uint8)
+    assert gb.encode_rgb24_host(gb.ETC1_FLOATREF, out, rgb_of(img, w, h).reshape(-1), w, h, w * 3) == 0
+    assert np.array_equal(out, reference.compress_float_reference(ETC1, img, w, h)[1])
+    # argument checks: the codec's shape rules first, then the packed-row rules
+    buf = np.zeros(64 * 64 * 3, dtype=np.uint8)
+    assert gb.encode_rgb24_host(DXT1, out, buf, 24, 32, 72) == -1
+    assert gb.encode_rgb24_host(DXT1, out, buf, 32, 30, 96) == -2
+    assert gb.encode_rgb24_host(DXT1, out, buf, 0, 0, 0) == 0
+    assert gb.encode_rgb24_host(DXT1, out, buf, 32, 32, 92) == -5
+    assert gb.encode_rgb24_host(DXT1, out, buf, 32, 32, 98) == -4
+    assert gb.encode_rgb24_host(DXT1, out, None, 32, 32, 96) == -3
+    assert gb.encode_rgb24_host(gb.BOTH, out, buf, 32, 32, 96) == -3
+    assert gb.encode_rgb24_host(9, out, buf, 32, 32, 96) == -6
