@@ -193,14 +193,13 @@ int goofy_b200_encode_relaxed_device(int codec, void* d_result, const void* d_in
     const uint8_t* src = (const uint8_t*)d_input;
     uint8_t* dst = (uint8_t*)d_result;
     t_lastKernel = "encode_relaxed_kernel";
+    const dim3 block(256, 1, 1);
     switch (codec) {
-        case GOOFY_B200_DXT1: gb::encode_relaxed_kernel<gb::kDxt1, 0><<<grid, 256, 0, s>>>(src, dst, width, height, stride); break;
-        case GOOFY_B200_ETC1: gb::encode_relaxed_kernel<gb::kEtc1, 0><<<grid, 256, 0, s>>>(src, dst, width, height, stride); break;
-        case GOOFY_B200_DXT1_FLOATREF: gb::encode_relaxed_kernel<gb::kDxt1, 1><<<grid, 256, 0, s>>>(src, dst, width, height, stride); break;
-        default: gb::encode_relaxed_kernel<gb::kEtc1, 1><<<grid, 256, 0, s>>>(src, dst, width, height, stride); break;
+        case GOOFY_B200_DXT1: return launch_pdl(gb::encode_relaxed_kernel<gb::kDxt1, 0>, grid, block, s, src, dst, width, height, stride);
+        case GOOFY_B200_ETC1: return launch_pdl(gb::encode_relaxed_kernel<gb::kEtc1, 0>, grid, block, s, src, dst, width, height, stride);
+        case GOOFY_B200_DXT1_FLOATREF: return launch_pdl(gb::encode_relaxed_kernel<gb::kDxt1, 1>, grid, block, s, src, dst, width, height, stride);
+        default: return launch_pdl(gb::encode_relaxed_kernel<gb::kEtc1, 1>, grid, block, s, src, dst, width, height, stride);
     }
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cuda_rc(cudaGetLastError());
 }
 
 int goofy_b200_decode_device(int codec, void* d_rgba, const void* d_blocks, uint32_t width, uint32_t height, uint32_t stride,
@@ -225,10 +224,8 @@ int goofy_b200_decode_device(int codec, void* d_rgba, const void* d_blocks, uint
     P.bh = height / 4u;
     P.stride = stride;
     const dim3 grid((P.bw + 255u) / 256u, P.bh, 1);
-    if (codec == GOOFY_B200_DXT1) gb::decode_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
-    else gb::decode_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cuda_rc(cudaGetLastError());
+    return codec == GOOFY_B200_DXT1 ? launch_pdl(gb::decode_kernel<0>, grid, dim3(256, 1, 1), (cudaStream_t)stream, P)
+                                    : launch_pdl(gb::decode_kernel<1>, grid, dim3(256, 1, 1), (cudaStream_t)stream, P);
 }
 
 int goofy_b200_block_sse_device(int codec, const void* d_blocks, const void* d_rgba, uint32_t width, uint32_t height,
@@ -269,10 +266,8 @@ int goofy_b200_block_sse_device(int codec, const void* d_blocks, const void* d_r
     if (gy < 1u) gy = 1u;
     if (gy > P.bh) gy = P.bh;
     const dim3 grid(gx, gy, 1);
-    if (codec == GOOFY_B200_DXT1) gb::block_sse_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
-    else gb::block_sse_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cuda_rc(cudaGetLastError());
+    return codec == GOOFY_B200_DXT1 ? launch_pdl(gb::block_sse_kernel<0>, grid, dim3(256, 1, 1), (cudaStream_t)stream, P)
+                                    : launch_pdl(gb::block_sse_kernel<1>, grid, dim3(256, 1, 1), (cudaStream_t)stream, P);
 }
 
 int goofy_b200_encode_batch_device(int codec, const GoofyB200Image* descs, uint32_t n_images, void* stream)

@@ -43,6 +43,8 @@ __device__ __forceinline__ void store_row(uint8_t* p, uint32_t a, uint32_t b, ui
 template <int CODEC>
 __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams P)
 {
+    pdl_launch_dependents();   // programmatic dependent launch, as in the encoders (encode_kernels.cuh)
+    pdl_wait();
     const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
     if (bx >= P.bw) return;
     const uint2 blk = load_block(P.blocks + ((uint64_t)by * P.bw + bx) * 8u);
@@ -63,6 +65,8 @@ template <int CODEC>
 __global__ void __launch_bounds__(256) block_sse_kernel(const DecodeParams P)
 {
     __shared__ uint32_t partial[8][3];
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t bx = blockIdx.x * 256u + threadIdx.x;
     uint32_t sr = 0, sg = 0, sb = 0;
     if (bx < P.bw) {

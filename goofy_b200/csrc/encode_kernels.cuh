@@ -366,10 +366,10 @@ template <int CODEC, bool ROWS>
 __global__ void __launch_bounds__(256, CODEC == kDxt1 ? 8 : 6) encode_floatref_kernel(const EncodeParams P)
 {
     __shared__ uint32_t lut[CODEC == kDxt1 ? 1 : 256];
-    if (CODEC != kDxt1) {
-        stage_control_lut<true, 256>(lut, threadIdx.y * blockDim.x + threadIdx.x);
-        __syncthreads();
-    }
+    pdl_launch_dependents();
+    if (CODEC != kDxt1) stage_control_lut<true, 256>(lut, threadIdx.y * blockDim.x + threadIdx.x);
+    pdl_wait();
+    if (CODEC != kDxt1) __syncthreads();
     const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t by = P.by0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (bx >= P.bw || by >= P.bh) return;
@@ -454,10 +454,10 @@ __global__ void __launch_bounds__(256, CODEC == kDxt1 ? 6 : GB_RELAXED_ETC1_CTAS
 {
     constexpr bool ROWS = CODEC != kDxt1;   // DXT1 flavours: one-shot CTAs (gridDim.y = block rows)
     __shared__ uint32_t lut[CODEC == kDxt1 ? 1 : 256];
-    if (CODEC != kDxt1) {
-        stage_control_lut<FLAVOUR != 0, 256>(lut, threadIdx.x);
-        __syncthreads();
-    }
+    pdl_launch_dependents();
+    if (CODEC != kDxt1) stage_control_lut<FLAVOUR != 0, 256>(lut, threadIdx.x);
+    pdl_wait();
+    if (CODEC != kDxt1) __syncthreads();
     const uint32_t bw = (width + 3u) / 4u, bh = (height + 3u) / 4u;
     const uint32_t bx = blockIdx.x * 256u + threadIdx.x;
     if (bx >= bw) return;
@@ -540,10 +540,10 @@ __global__ void __launch_bounds__(kBatchTileX* kBatchTileY, ctas_per_sm(MODE))
     encode_batch_kernel(const __grid_constant__ TABLE table, uint32_t nImages)
 {
     __shared__ uint32_t lut[MODE == kDxt1 ? 1 : 256];
-    if (MODE != kDxt1) {
-        stage_control_lut<FLAVOUR != 0, kBatchTileX * kBatchTileY>(lut, threadIdx.y * kBatchTileX + threadIdx.x);
-        __syncthreads();
-    }
+    pdl_launch_dependents();
+    if (MODE != kDxt1) stage_control_lut<FLAVOUR != 0, kBatchTileX * kBatchTileY>(lut, threadIdx.y * kBatchTileX + threadIdx.x);
+    pdl_wait();   // (the descriptor table of a large batch is global memory written by a copy earlier in the stream)
+    if (MODE != kDxt1) __syncthreads();
     // largest i with start(i) <= blockIdx.x
     uint32_t lo = 0, hi = nImages;
     while (hi - lo > 1u) {

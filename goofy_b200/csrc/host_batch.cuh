@@ -10,9 +10,7 @@ template <int MODE, int FLAVOUR, typename TABLE>
 int launch_batch(const TABLE& table, uint32_t n, uint32_t totalCtas, cudaStream_t stream)
 {
     t_lastKernel = MODE == gb::kDxt1 ? "encode_batch_kernel<dxt1>" : MODE == gb::kEtc1 ? "encode_batch_kernel<etc1s>" : "encode_batch_kernel<dxt1+etc1s>";
-    gb::encode_batch_kernel<MODE, FLAVOUR, TABLE><<<totalCtas, dim3(gb::kBatchTileX, gb::kBatchTileY, 1), 0, stream>>>(table, n);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cuda_rc(cudaGetLastError());
+    return launch_pdl(gb::encode_batch_kernel<MODE, FLAVOUR, TABLE>, dim3(totalCtas, 1, 1), dim3(gb::kBatchTileX, gb::kBatchTileY, 1), stream, table, n);
 }
 
 // codec: DXT1, ETC1, BOTH, or a float-reference flavour

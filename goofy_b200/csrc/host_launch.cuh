@@ -25,6 +25,27 @@ int launch_encode(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, con
     return cuda_rc(e);
 }
 
+// Any kernel of this library with programmatic stream serialisation: every one of them starts with
+// griddepcontrol.launch_dependents and waits (griddepcontrol.wait) before it touches global memory.
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args)
+{
+    static const bool pdl = []() { const char* e = getenv("GOOFY_B200_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(e);
+}
+
 template <int MODE>
 constexpr const char* kernel_name(const char* dxt1, const char* etc1, const char* dual) { return MODE == gb::kDxt1 ? dxt1 : MODE == gb::kEtc1 ? etc1 : dual; }
 #define GB_KNAME(base) kernel_name<MODE>(base "<dxt1>", base "<etc1s>", base "<dxt1+etc1s>")
@@ -445,9 +466,8 @@ int encode_floatref(int codec, void* dst, const void* src, uint32_t width, uint3
             Q.src += (uint64_t)img0 * srcPitch;
             Q.dst += (uint64_t)img0 * dstPitch;
             t_lastKernel = "encode_floatref_kernel<etc1s, row-walking>";
-            gb::encode_floatref_kernel<gb::kEtc1, true><<<dim3(gx, gy, nz), block, 0, stream>>>(Q);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            GB_CUDA(cudaGetLastError());
+            const int rc = launch_pdl(gb::encode_floatref_kernel<gb::kEtc1, true>, dim3(gx, gy, nz), block, stream, Q);
+            if (rc != GOOFY_B200_OK) return rc;
         }
         return GOOFY_B200_OK;
     }
@@ -462,9 +482,8 @@ int encode_floatref(int codec, void* dst, const void* src, uint32_t width, uint3
             Q.dst += (uint64_t)img0 * dstPitch;
             const dim3 grid(gx, (rows + ty - 1u) / ty, nz);
             t_lastKernel = "encode_floatref_kernel<dxt1>";
-            gb::encode_floatref_kernel<gb::kDxt1, false><<<grid, block, 0, stream>>>(Q);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            GB_CUDA(cudaGetLastError());
+            const int rc = launch_pdl(gb::encode_floatref_kernel<gb::kDxt1, false>, grid, block, stream, Q);
+            if (rc != GOOFY_B200_OK) return rc;
         }
     }
     return GOOFY_B200_OK;
