@@ -209,7 +209,10 @@ int run_hybrid(int codec, const HostJob& J, ThreadResources& R, int dev)
         for (int i = 0; i < kFlights; ++i) {
             if (!flight[i].busy) continue;
             const cudaError_t e = cudaEventQuery(R.pipe.uploaded[i]);
-            if (e == cudaErrorNotReady) continue;
+            if (e == cudaErrorNotReady) {
+                cudaGetLastError();   // "not ready" is recorded as the thread's last error: do not leave it for the caller's next check
+                continue;
+            }
             if (e != cudaSuccess) return cuda_rc(e);
             flight[i].busy = false;
             queuedBytes -= flight[i].bytes;
