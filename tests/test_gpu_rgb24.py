@@ -233,6 +233,18 @@ def test_hybrid_scheduler_splits_the_image(rgb_mode, reference):
         else:
             assert d["plain_calls"] >= 2
         print(f"mode {mode}: {d}, {gb.host_threads()} host threads")
+    # the scheduler polls events: "not ready" must not be left behind as the calling thread's last CUDA error
+    import ctypes as C
+    from goofy_b200 import _lib
+    _lib.load()
+    rt = None
+    for line in open("/proc/self/maps"):
+        if "libcudart.so" in line and "torch" not in line:
+            rt = C.CDLL(line.split()[-1])   # the runtime libgoofy_b200.so is linked against (already loaded)
+            break
+    if rt is not None:
+        assert rt.cudaPeekAtLastError() == 0
+    assert float((torch.zeros(4, device="cuda") + 1).sum()) == 4.0
 
 
 def test_rgb24_host_call(reference):
