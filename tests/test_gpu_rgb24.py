@@ -282,3 +282,38 @@ def test_rgb24_host_call(reference):
     assert gb.encode_rgb24_host(DXT1, out, None, 32, 32, 96) == -3
     assert gb.encode_rgb24_host(gb.BOTH, out, buf, 32, 32, 96) == -3
     assert gb.encode_rgb24_host(9, out, buf, 32, 32, 96) == -6
+
+
+def test_host_calls_from_concurrent_threads_with_packing(rgb_mode, reference):
+    """Four host threads inside the host path at once, every one on its own large pinned image with packing forced: the
+    copy pool serialises their staging jobs, every thread has its own pack ring, events and device strips."""
+    import threading
+    gb.set_host_rgb_staging(gb.HOST_RGB_ALWAYS)
+    w, h = 4096, 2304
+    imgs = [aligned_copy(synth_family(i % 4, w, h, seed=40 + i)) for i in range(4)]
+    pinned = [_pinned(im) for im in imgs]
+    outs = [torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory() for _ in imgs]
+    pageable_outs = [np.zeros(w * h // 2, dtype=np.uint8) for _ in imgs]
+    want = [reference.compress_mt(DXT1 if i % 2 == 0 else ETC1, imgs[i], w, h, w * 4, 8)[1] for i in range(4)]
+    errors = []
+
+    def work(i):
+        fn = gb.compressDXT1 if i % 2 == 0 else gb.compressETC1
+        try:
+            for _ in range(3):
+                if fn(outs[i], pinned[i], w, h, w * 4) != 0:
+                    errors.append((i, "pinned rc"))
+                if fn(pageable_outs[i], imgs[i], w, h, w * 4) != 0:      # pageable input: packed while it is staged
+                    errors.append((i, "pageable rc"))
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i in range(4):
+        assert np.array_equal(outs[i].numpy(), want[i]), i
+        assert np.array_equal(pageable_outs[i], want[i]), i
