@@ -172,7 +172,7 @@ int make_host_job(int codec, void* result, const void* input, uint32_t width, ui
 // calls with and without packing: the cost of its packing falls on the OTHER ranks, so each of them measures packing
 // as the better reply to what the others do, and all of them settle on the worse state (tried: session T).  What a
 // process can see is the rate of its own PLAIN uploads: a B200 link (PCIe Gen5 x16) carries a plain call at 53-54
-// GB/s of input when nothing else holds it back, so AUTO packs only while its plain calls reach kHybridMinPlainGBs (40 GB/s)
+// GB/s of input when nothing else holds it back, so AUTO packs only while its plain calls reach kHybridMinPlainGBs (48 GB/s)
 // (GOOFY_B200_HYBRID_MIN_LINK_GBS) and -- belt and braces -- while calls that pack measure faster than calls that do
 // not.  Every thread's first two calls are plain (the first one cold and not recorded); later every sixteenth call
 // runs the way that is NOT preferred to keep both means current.  The bytes produced are the same either way.

@@ -5,9 +5,8 @@
 
 namespace {
 
-// A B200 link (PCIe Gen5 x16) carries a plain host call at 53-54 GB/s of input when nothing else holds it back (47 on one
-// box with a slow host, where packing still took the call from 5.7 to 4.4 ms); four ranks uploading at once get 27-35 each.
-constexpr int kHybridMinPlainGBs = 40;
+// A B200 link (PCIe Gen5 x16) carries a plain host call at 53-54 GB/s of input when nothing else holds it back.
+constexpr int kHybridMinPlainGBs = 48;
 
 // One per calling thread.  next() decides whether the coming call on a large pinned image packs (alpha-stripped strips
 // from the back of the image) or runs as plain DMA; record() takes the input rate the call then achieved.

@@ -33,20 +33,20 @@ static int run(HybridChoice& c, const Host& h, int calls, bool firstCold = true)
 int main()
 {
     {   // one process, link-bound host: plain 53.6 GB/s, packing 61 GB/s -> packs, except the first two calls and one probe in sixteen
-        HybridChoice c((double)kHybridMinPlainGBs * 1e9);
+        HybridChoice c(48e9);
         const Host h{53.6e9, 61e9};
         CHECK(run(c, h, 2) == 0);
         CHECK(run(c, h, 62, false) == 62 - 4);   // calls 15, 31, 47, 63 probe the plain pipeline
         CHECK(c.ratePlain > 53e9 && c.ratePlain < 54e9);   // the cold first call never entered the mean
     }
     {   // one process per GPU on a shared host: plain uploads reach 35 GB/s -> never packs, whatever packing would measure
-        HybridChoice c((double)kHybridMinPlainGBs * 1e9);
+        HybridChoice c(48e9);
         CHECK(run(c, Host{35e9, 40e9}, 100) == 0);
         // ... the other ranks finish: plain calls reach link rate again, packing resumes
         CHECK(run(c, Host{53.6e9, 61e9}, 40, false) >= 30);
     }
     {   // link-bound, but packing is slower on this host (few cores): tries it once, then only probes
-        HybridChoice c((double)kHybridMinPlainGBs * 1e9);
+        HybridChoice c(48e9);
         const int packed = run(c, Host{53.6e9, 45e9}, 66);
         CHECK(packed >= 1 && packed <= 1 + 4);
     }
