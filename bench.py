@@ -336,11 +336,8 @@ class Ctx:
         if self.distributed and "GOOFY_B200_HOST_THREADS" not in os.environ:
             local_world = int(os.environ.get("LOCAL_WORLD_SIZE", self.world))
             os.environ["GOOFY_B200_HOST_THREADS"] = str(max(2, min(8, (os.cpu_count() or 8) // max(1, local_world))))
-        # ... and pinned input goes plain DMA: the alpha-stripping of one rank loads the host memory every rank uploads
-        # from, which no rank sees in its own timings (include/goofy_b200.h: GOOFY_B200_HOST_RGB_PAGEABLE; 2 ranks measured
-        # +6 % on one box and -12 % on another, 4 ranks -12...-18 %; profiles/r02_rgb24_sessions.md)
-        if self.distributed and "GOOFY_B200_HOST_RGB" not in os.environ:
-            os.environ["GOOFY_B200_HOST_RGB"] = "3"
+        # (whether pinned input is alpha-stripped is the library's call: with other ranks' processes on the box's GPUs it
+        # sees neighbours -- goofy_b200_host_neighbours, reported in e2e.host_neighbours -- and leaves pinned input to plain DMA)
         from goofy_b200 import _lib
         self.lib = _lib.load()          # raw ctypes entry points: pointers and the stream as plain integers, so a
         self.stream = int(torch.cuda.current_stream().cuda_stream)   # 20 us launch is not waiting for Python
@@ -823,7 +820,7 @@ def run_b200_arm(args):
                "host_rgb_staging": {0: "off", 1: "auto", 2: "always", 3: "pageable input only (one process per GPU on a shared host)"}[mode],
                "alpha_stripped_share_of_pixels": (size * size * 4 - h2d_actual) / (size * size),   # a stripped pixel saves one byte
                "calls_with_packing": link1["packing_calls"] - link0["packing_calls"], "calls_plain_dma": link1["plain_calls"] - link0["plain_calls"],
-               "host_threads": gb.host_threads(),
+               "host_threads": gb.host_threads(), "host_neighbours": gb.host_neighbours(),
                "rgba_dma_only": {"value": size * size * e2e_steps * world / (ms_raw * 1e-3) / 1e6, "unit": "MP/s",
                                  "ms_per_step": ms_raw / e2e_steps, "h2d_bytes_per_step": size * size * 4,
                                  "note": "same call, goofy_b200_set_host_rgb_staging(OFF): the plain strip pipeline of round 1"},

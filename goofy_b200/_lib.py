@@ -40,6 +40,7 @@ PROTOTYPES = {
     "goofy_b200_set_host_rgb_staging": (_int, [_int]),
     "goofy_b200_get_host_rgb_staging": (_int, []),
     "goofy_b200_host_threads": (_int, []),
+    "goofy_b200_host_neighbours": (_int, []),
     "goofy_b200_host_link_stats": (None, [C.POINTER(_u64)] * 5),
     "goofy_b200_compress_dxt1": (_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_uint]),
     "goofy_b200_compress_etc1": (_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_uint]),

@@ -86,6 +86,11 @@ def host_threads() -> int:
     return int(_lib.load().goofy_b200_host_threads())
 
 
+def host_neighbours() -> int:
+    """GPUs of this box that run somebody else's compute process (-1: cannot tell); AUTO packs pinned input only at 0."""
+    return int(_lib.load().goofy_b200_host_neighbours())
+
+
 def host_link_stats() -> dict:
     """Bytes the host path sent host -> device so far, and raw / alpha-stripped strips of large pinned images."""
     b, r, p, pc, nc = (C.c_uint64() for _ in range(5))

@@ -11,7 +11,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libgoofy_b200.so"
 SOURCES = [CSRC / "capi.cu"]
 HEADERS = [CSRC / "lanes.cuh", CSRC / "block_codec.cuh", CSRC / "encode_kernels.cuh", CSRC / "tma_kernels.cuh", CSRC / "decode_kernels.cuh",
-           CSRC / "block_decode.cuh", CSRC / "copy_pool.h", CSRC / "rgb_pack.h", CSRC / "hybrid_choice.h",
+           CSRC / "block_decode.cuh", CSRC / "copy_pool.h", CSRC / "rgb_pack.h", CSRC / "hybrid_choice.h", CSRC / "host_neighbours.cuh",
            CSRC / "host_common.cuh", CSRC / "host_launch.cuh", CSRC / "host_resources.cuh", CSRC / "host_pipeline.cuh", CSRC / "host_batch.cuh",
            PKG_DIR.parent / "include" / "goofy_b200.h"]
 

@@ -9,6 +9,7 @@
 // and everything is compiled as ONE translation unit (the kernels' __device__ tables live in it).
 // All arithmetic lives in block_codec.cuh.  There is no CPU encoder anywhere in this library:
 // without a CUDA device every call returns an error code.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -68,6 +69,8 @@ int goofy_b200_set_host_rgb_staging(int mode)
 int goofy_b200_get_host_rgb_staging(void) { return host_rgb_mode(); }
 
 int goofy_b200_host_threads(void) { return (int)CopyPool::get().threads(); }
+
+int goofy_b200_host_neighbours(void) { return Neighbours::count(); }
 
 void goofy_b200_host_link_stats(uint64_t* bytes_uploaded, uint64_t* raw_strips, uint64_t* packed_strips, uint64_t* packing_calls,
                                 uint64_t* plain_calls)

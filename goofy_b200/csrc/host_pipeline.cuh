@@ -4,6 +4,7 @@
 #include "host_resources.cuh"
 #include "copy_pool.h"
 #include "hybrid_choice.h"
+#include "host_neighbours.cuh"
 
 namespace {
 
@@ -500,7 +501,7 @@ int run_host_jobs(int codec, const HostJob* jobs, uint32_t nJobs, int dev)
         if (!J.rgbSource && !J.stageIn && !J.stageOut && !J.stageOut2 && J.blockRows != 0u &&
             (host_rgb_mode() == GOOFY_B200_HOST_RGB_AUTO || host_rgb_mode() == GOOFY_B200_HOST_RGB_ALWAYS) &&
             (size_t)J.blockRows * 4u * J.rowBytes > zeroCopyMax) {
-            const bool packing = host_rgb_mode() == 2 || t_hybridChoice.next();
+            const bool packing = host_rgb_mode() == 2 || t_hybridChoice.next(Neighbours::count());
             (packing ? g_packingCalls : g_plainCalls).fetch_add(1, std::memory_order_relaxed);
             if (packing) {
                 for (int i = 0; i < kSlots; ++i, slot = (slot + 1) % kSlots) {

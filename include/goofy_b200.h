@@ -106,13 +106,15 @@ int goofy_b200_get_load_path(void);
  * are input).  Process-wide; set returns the previous setting (or GOOFY_B200_E_ARGS).
  *   OFF     every pixel crosses the link as RGBA
  *   AUTO    (default) pageable input is staged as packed RGB -- the staging copy is made anyway; large pinned input is
- *           split between plain DMA and alpha-stripped strips according to how fast the host's cores pack, and only
- *           while calls that pack measure faster than calls that do not (one process per GPU on a shared host can be
- *           bound by host memory instead of by the link; packing then loses and AUTO stops doing it)
+ *           split between plain DMA and alpha-stripped strips according to how fast the host's cores pack -- while no
+ *           other GPU of the box runs somebody else's compute process (goofy_b200_host_neighbours: one process per
+ *           GPU on a shared host is bound by host memory, not by the link, and packing then makes everybody slower) and
+ *           while calls that pack measure faster than calls that do not
  *   ALWAYS  every strip of a large pinned image is alpha-stripped first (experiments)
- *   PAGEABLE  pageable input only; pinned input always goes plain DMA.  What a launcher that runs ONE PROCESS PER GPU
- *           on a shared host should set: the packing of one rank loads the host memory all ranks upload from, which
- *           no rank can see in its own measurements (2 ranks: +6 % on one box, -12 % on another; 4 ranks -12...-18 %)
+ *   PAGEABLE  pageable input only; pinned input always goes plain DMA.  For launchers that run ONE PROCESS PER GPU on a
+ *           shared host where NVML is not available to AUTO: the packing of one rank loads the host memory all ranks
+ *           upload from, which no rank can see in its own measurements (2 ranks: +6 % on one box, -12 % on another;
+ *           4 ranks -12...-22 %)
  * The bytes produced are identical in every mode.  Environment: GOOFY_B200_HOST_RGB=0|1|2|3 (initial mode),
  * GOOFY_B200_HOST_THREADS=n (host threads per staging job, the caller included; default min(8, cores / 2)). */
 #define GOOFY_B200_HOST_RGB_OFF 0
@@ -123,6 +125,10 @@ int goofy_b200_set_host_rgb_staging(int mode);
 int goofy_b200_get_host_rgb_staging(void);
 /* Host threads that work on one staging job (copy or alpha strip), the calling thread included. */
 int goofy_b200_host_threads(void);
+/* GPUs of this box that run somebody else's compute process, as AUTO sees them (NVML, all GPUs whatever
+ * CUDA_VISIBLE_DEVICES says; this process's own contexts do not count); -1 = cannot tell (no NVML).  With neighbours AUTO
+ * never alpha-strips pinned input: their uploads share the host's memory system with the packing. */
+int goofy_b200_host_neighbours(void);
 /* What the host path sent over the link so far in this process (all threads): bytes host -> device (copy engine and
  * zero-copy kernel reads); strips of large pinned images sent as they were / alpha-stripped first; calls on large pinned
  * images that ran with packing / as plain DMA (AUTO measures both and uses the faster).  Any pointer may be NULL. */

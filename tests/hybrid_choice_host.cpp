@@ -9,11 +9,11 @@ struct Host {
 };
 
 // runs `calls` calls, returns how many packed; `firstCold`: the very first call is three times slower
-static int run(HybridChoice& c, const Host& h, int calls, bool firstCold = true)
+static int run(HybridChoice& c, const Host& h, int calls, bool firstCold = true, int neighbours = -1)
 {
     int packed = 0;
     for (int i = 0; i < calls; ++i) {
-        const bool p = c.next();
+        const bool p = c.next(neighbours);
         packed += p;
         double rate = p ? h.packing : h.plain;
         if (firstCold && c.calls == 1u) rate /= 3.0;
@@ -53,6 +53,15 @@ int main()
     {   // the gate can be lowered (GOOFY_B200_HYBRID_MIN_LINK_GBS) for slower links
         HybridChoice c(20e9);
         CHECK(run(c, Host{26e9, 30e9}, 34) >= 28);
+    }
+    {   // neighbours counted (NVML): with any, never; alone, even a slow link packs (the gate is for the "cannot tell" case)
+        HybridChoice c((double)kHybridMinPlainGBs * 1e9);
+        CHECK(run(c, Host{51.5e9, 60e9}, 40, true, 1) == 0);
+        CHECK(run(c, Host{51.5e9, 60e9}, 40, false, 3) == 0);
+        HybridChoice d((double)kHybridMinPlainGBs * 1e9);
+        CHECK(run(d, Host{47e9, 60e9}, 34, true, 0) >= 28);
+        HybridChoice e((double)kHybridMinPlainGBs * 1e9);
+        CHECK(run(e, Host{47e9, 60e9}, 34, true, -1) == 0);
     }
     std::printf("ok\n");
     return 0;

@@ -317,3 +317,41 @@ def test_host_calls_from_concurrent_threads_with_packing(rgb_mode, reference):
     for i in range(4):
         assert np.array_equal(outs[i].numpy(), want[i]), i
         assert np.array_equal(pageable_outs[i], want[i]), i
+
+
+def test_host_neighbours_sees_another_process():
+    """AUTO asks NVML whether some GPU of the box runs somebody else's compute process (this process's own contexts do
+    not count): alone -> 0; with a second process holding a context -> at least 1, and AUTO then leaves pinned input to
+    plain DMA; after it has gone -> 0 again (the answer is refreshed every few seconds)."""
+    import subprocess
+    import sys
+    import time
+    torch.zeros(1, device="cuda")
+    n0 = gb.host_neighbours()
+    if n0 < 0:
+        pytest.skip("NVML not available: the host path falls back to its rate gate")
+    assert n0 == 0, "this test needs the box to itself"
+    child = subprocess.Popen([sys.executable, "-c", "import torch, sys, time; torch.zeros(1, device='cuda'); print('up', flush=True); time.sleep(60)"],
+                             stdout=subprocess.PIPE, text=True)
+    try:
+        assert child.stdout.readline().strip() == "up"
+        deadline = time.time() + 10
+        while gb.host_neighbours() == 0 and time.time() < deadline:
+            time.sleep(0.5)
+        assert gb.host_neighbours() >= 1
+        before = gb.host_link_stats()
+        gb.set_host_rgb_staging(gb.HOST_RGB_AUTO)
+        w, h = 8192, 2048
+        img = torch.from_numpy(synth_family(1, w, h, seed=3).reshape(-1)).pin_memory()
+        out = torch.zeros(w * h // 2, dtype=torch.uint8).pin_memory()
+        for _ in range(6):
+            assert gb.compressDXT1(out, img, w, h, w * 4) == 0
+        after = gb.host_link_stats()
+        assert after["packing_calls"] == before["packing_calls"] and after["plain_calls"] - before["plain_calls"] == 6
+    finally:
+        child.kill()
+        child.wait()
+    deadline = time.time() + 10
+    while gb.host_neighbours() != 0 and time.time() < deadline:
+        time.sleep(0.5)
+    assert gb.host_neighbours() == 0
