@@ -330,7 +330,8 @@ def test_host_neighbours_sees_another_process():
     n0 = gb.host_neighbours()
     if n0 < 0:
         pytest.skip("NVML not available: the host path falls back to its rate gate")
-    assert n0 == 0, "this test needs the box to itself"
+    if n0 != 0:
+        pytest.skip(f"{n0} GPU(s) of this box already run somebody else's compute process: the test needs the box to itself")
     child = subprocess.Popen([sys.executable, "-c", "import torch, sys, time; torch.zeros(1, device='cuda'); print('up', flush=True); time.sleep(60)"],
                              stdout=subprocess.PIPE, text=True)
     try:
