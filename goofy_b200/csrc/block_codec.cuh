@@ -39,6 +39,18 @@ GB_DEV uint32_t reduce16(const uint32_t (&v)[16])
     return kMax ? max2_u16x2(t5, t6) : min2_u16x2(t5, t6);
 }
 
+// Packed RGB8 (3 bytes per pixel) -> the pixel words the codecs take: four pixels of one block row arrive as the three
+// words w0 = R0 G0 B0 R1 | w1 = G1 B1 R2 G2 | w2 = B2 R3 G3 B3.  Byte 3 of every result is whatever followed the pixel;
+// nothing below reads it (the dp4a weights of that byte are zero, the min / max lanes that carry it are never extracted).
+// Two byte permutes and a shift; tests/kernel_math_host.cpp runs every fixture through it on the host.
+GB_DEV void widen_rgb24(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t& p0, uint32_t& p1, uint32_t& p2, uint32_t& p3)
+{
+    p0 = w0;
+    p1 = prmt(w0, w1, 0x6543u);
+    p2 = prmt(w1, w2, 0x5432u);
+    p3 = w2 >> 8;
+}
+
 // Everything the two codecs share: bounding box and the per-block brightness scalars.
 struct BlockFront {
     // A u16 lane compare orders by its HIGH byte first, so the raw pixel word (lanes G:R | A:B)

@@ -411,7 +411,9 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t* p)
 __device__ __forceinline__ uint4 load_row_rgb24(const uint8_t* p)
 {
     const uint32_t w0 = load_word(p), w1 = load_word(p + 4), w2 = load_word(p + 8);
-    return make_uint4(w0, prmt(w0, w1, 0x6543u), prmt(w1, w2, 0x5432u), w2 >> 8);
+    uint4 px;
+    widen_rgb24(w0, w1, w2, px.x, px.y, px.z, px.w);   // block_codec.cuh
+    return px;
 }
 
 template <int MODE, int FLAVOUR>

@@ -15,6 +15,8 @@ extern "C" int kernel_math_compress(int codec, unsigned char* result, const unsi
 {
     const bool fused = (codec & 64) != 0;   // through encode_both (the dual-output kernel), DXT1 with the flag-byte scheme
     codec &= ~64;
+    const bool viaRgb24 = (codec & 128) != 0;   // the pixels take the packed-RGB kernels' way in: 3 bytes each, widened by widen_rgb24
+    codec &= ~128;
     const bool floatRef = (codec & 16) != 0;   // GOOFY_B200_FLOATREF flavours (codec 16 / 17); goofyRef accepts width % 4
     codec &= 15;
     if (width % (floatRef ? 4 : 16)) return -1;
@@ -25,6 +27,17 @@ extern "C" int kernel_math_compress(int codec, unsigned char* result, const unsi
         for (unsigned bx = 0; bx < width / 4; ++bx) {
             uint32_t p[16];
             for (int y = 0; y < 4; ++y) std::memcpy(&p[4 * y], input + (size_t)(4 * by + y) * stride + (size_t)bx * 16, 16);
+            if (viaRgb24) {
+                // what encode_rgb24_kernel sees: the block row's twelve bytes, with the bytes that FOLLOW in a packed row
+                // (the next block's first pixel, or padding) spilling into the unused byte of each pixel word
+                for (int y = 0; y < 4; ++y) {
+                    unsigned char packed[16] = {0xA5, 0xA5, 0xA5, 0xA5, 0xA5, 0xA5, 0xA5, 0xA5, 0xA5, 0xA5, 0xA5, 0xA5, 0xA5, 0xA5, 0xA5, 0xA5};
+                    for (int x = 0; x < 4; ++x) std::memcpy(packed + 3 * x, &p[4 * y + x], 3);
+                    uint32_t w[3];
+                    std::memcpy(w, packed, 12);
+                    gb::widen_rgb24(w[0], w[1], w[2], p[4 * y], p[4 * y + 1], p[4 * y + 2], p[4 * y + 3]);
+                }
+            }
             uint32_t w0, w1;
             if (floatRef) {
                 const gb::RefFront f = gb::analyse_ref(p, codec == 0 ? 32u : 64u);

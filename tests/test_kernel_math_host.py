@@ -31,6 +31,12 @@ def test_kernel_math_on_synthetic(codec, family, kernel_math, oracle):
     assert rc == 0 and np.array_equal(got, want)
     rc, got = kernel_math(codec | 64, img, 512, 512)   # through the fused dual-output encoder
     assert rc == 0 and np.array_equal(got, want)
+    # the packed-RGB kernels' way in (3 bytes per pixel, widened by widen_rgb24; byte 3 of every pixel word is junk)
+    for flags in (128, 128 | 64):
+        rc, got = kernel_math(codec | flags, img, 512, 512)
+        assert rc == 0 and np.array_equal(got, want), flags
+    rc, got = kernel_math(16 + codec + 128, img, 512, 512)   # float-reference flavour from packed RGB
+    assert rc == 0 and np.array_equal(got, oracle.compress_float_reference(codec, img, 512, 512)[1])
 
 
 @pytest.mark.parametrize("codec", CODECS)
